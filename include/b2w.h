@@ -1,0 +1,177 @@
+/*
+ * b2w.h -- C ABI of libb2w.so, the B200 (sm_100a) biased random-walk engine.
+ *
+ * This is the drop-in boundary for ONE hot path of krishnanlab/PecanPy: node2vec /
+ * node2vec+ walk generation behind pecanpy.pecanpy.{PreComp,SparseOTF,DenseOTF}
+ * .simulate_walks.  PecanPy has no FFI of its own (it is Python + Numba); the seam the
+ * entry points below replace is the call of the njit kernel `Base._random_walks`
+ * (reference src/pecanpy/pecanpy.py:149-157) and, for PreComp, the table builder
+ * `PreComp.preprocess_transition_probs` (pecanpy.py:442-507).  INTEGRATION.md shows the
+ * ctypes binding a PecanPy maintainer would add.
+ *
+ * Conventions
+ *   - Plain C: pointers, sizes, scalars.  No torch / C++ types cross this boundary.
+ *   - `d_*` pointers are DEVICE pointers owned by the caller (e.g. torch tensors); the
+ *     library borrows them for the duration of the call, or of the graph handle for
+ *     pointers passed to a *_create function.  `h_*` pointers are HOST pointers.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  All device
+ *     entry points are asynchronous with respect to the host unless stated otherwise.
+ *   - Every function returns B2W_OK (0) or a negative b2w_status; b2w_last_error()
+ *     returns a thread-local message for the last failure on the calling thread.
+ *   - A graph handle is read-only after creation: concurrent b2w_walk calls on
+ *     different streams are legal.
+ */
+#ifndef B2W_H_
+#define B2W_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2W_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+  B2W_OK = 0,
+  B2W_ERR_INVALID = -1,   /* bad argument */
+  B2W_ERR_CUDA = -2,      /* CUDA runtime error (message has the cudaError string) */
+  B2W_ERR_GRAPH = -3,     /* graph failed validation (unsorted / duplicate / negative / NaN) */
+  B2W_ERR_UNSUPPORTED = -4,
+  B2W_ERR_NOMEM = -5
+} b2w_status;
+
+/* Walk strategy: replaces the get_move_forward()/get_has_nbrs() closure pair that the
+ * reference passes into _random_walks (pecanpy.py:143-157; abstract in graph.py:99-105). */
+typedef enum {
+  B2W_MODE_SPARSE_OTF = 0,             /* pecanpy.py:510-561  SparseOTF            */
+  B2W_MODE_PRECOMP = 1,                /* pecanpy.py:364-507  PreComp              */
+  B2W_MODE_DENSE_OTF = 2,              /* pecanpy.py:564-614  DenseOTF             */
+  B2W_MODE_FIRST_ORDER_UNWEIGHTED = 3, /* pecanpy.py:293-309  FirstOrderUnweighted */
+  B2W_MODE_PRECOMP_FIRST_ORDER = 4     /* pecanpy.py:312-361  PreCompFirstOrder    */
+} b2w_mode;
+
+/* Random-number regime. */
+typedef enum {
+  /* Philox4x32-10, key = (seed lo, seed hi), counter = (row lo, row hi, step, block):
+   * the production regime; output is independent of grid, thread and GPU count. */
+  B2W_RNG_PHILOX = 0,
+  /* Caller-fed uniforms U[row - row0, step - 1] (double, row-major, leading dim =
+   * walk_length): replays the reference's MT19937 stream (regime R1).  OTF modes only. */
+  B2W_RNG_FEED = 1
+} b2w_rng;
+
+/* b2w_walk flags */
+#define B2W_FLAG_FORCE_EXACT_REPLAY 0x1u /* test hook: always take the sequential replay path */
+#define B2W_FLAG_NO_FILTER_STATS 0x2u    /* do not update the fallback counters */
+#define B2W_FLAG_THREAD_PER_WALKER 0x4u  /* SparseOTF: use the lane-per-walker kernel */
+
+typedef struct b2w_graph b2w_graph; /* opaque */
+
+typedef struct {
+  uint32_t num_nodes;
+  uint64_t nnz;
+  uint32_t max_degree;
+  uint32_t flags; /* B2W_GRAPH_* */
+} b2w_graph_info;
+
+#define B2W_GRAPH_CSR 0x1u
+#define B2W_GRAPH_DENSE 0x2u
+#define B2W_GRAPH_UNWEIGHTED 0x4u /* every stored weight == 1.0f */
+#define B2W_GRAPH_HAS_ALIAS 0x8u
+
+typedef struct {
+  uint64_t steps;            /* walk steps taken (sum of effective_length - 1)           */
+  uint64_t exact_replays;    /* OTF steps whose parallel filter was inconclusive         */
+  uint64_t seq_sums;         /* OTF steps whose normaliser needed the sequential f32 sum */
+  uint64_t overflow_choices; /* steps that reproduced the reference's choice == degree   */
+} b2w_walk_stats;
+
+int b2w_version(void);
+const char* b2w_last_error(void);
+int b2w_device_count(int* out);
+
+/* ---- graph handles ---------------------------------------------------------------------
+ * CSR layout of the reference (typing.py:31, graph.py:323-341): indptr u32[n+1],
+ * indices u32[nnz] with every row sorted ascending and duplicate-free, data f32[nnz].
+ * `d_indices` MUST have room for nnz+1 elements: element [nnz] is read (never written)
+ * when the reference's unchecked `indices[indptr[cur] + choice]` (pecanpy.py:559) is hit with
+ * choice == degree on the last non-empty row; set it to 0.
+ * Validation (sortedness, uniqueness, weights finite and >= 0) runs on the device and
+ * synchronises the stream once.  Replaces: SparseGraph members read as closure constants in
+ * pecanpy.py:397-399,535-537. */
+int b2w_graph_csr_create(int device, uint32_t num_nodes, uint64_t nnz, const uint32_t* d_indptr,
+                         const uint32_t* d_indices, const float* d_data, b2w_graph** out);
+
+/* Dense layout of the reference (graph.py:576-580): data f64[n,n] row-major, nonzero
+ * u8/bool[n,n] == (data != 0).  Weights must be finite and >= 0.
+ * Replaces: DenseGraph members read in pecanpy.py:589-590. */
+int b2w_graph_dense_create(int device, uint32_t num_nodes, const double* d_data,
+                           const uint8_t* d_nonzero, b2w_graph** out);
+
+int b2w_graph_info_get(const b2w_graph* g, b2w_graph_info* out);
+void b2w_graph_destroy(b2w_graph* g);
+
+/* ---- PreComp alias tables --------------------------------------------------------------
+ * Replaces PreComp.preprocess_transition_probs (pecanpy.py:442-507) + alias_setup
+ * (pecanpy.py:617-665).  The caller computes alias_indptr = [0, cumsum(deg^2)] as u64[n+1]
+ * (pecanpy.py:474-476) and allocates d_alias_j u32 / d_alias_q f32 with alias_indptr[n] +
+ * max_degree elements (the slack is only read, after the reference's failed neighbour search,
+ * pecanpy.py:429-434).  `d_thr` (f32[n], get_noise_thresholds, rw/sparse_rw.py:22-35) is
+ * required when extend != 0.  `d_work`/`work_bytes`: scratch, at least
+ * b2w_alias_build_work_bytes(g) bytes.  Output is bit-identical to the reference's arrays. */
+size_t b2w_alias_build_work_bytes(const b2w_graph* g);
+int b2w_alias_build(const b2w_graph* g, double p, double q, int extend, const float* d_thr,
+                    const uint64_t* d_alias_indptr, uint32_t* d_alias_j, float* d_alias_q,
+                    void* d_work, size_t work_bytes, void* stream);
+
+/* PreCompFirstOrder tables (pecanpy.py:336-361): one table per node, laid out like `data`. */
+int b2w_alias_build_first_order(const b2w_graph* g, uint32_t* d_alias_j, float* d_alias_q,
+                                void* d_work, size_t work_bytes, void* stream);
+
+/* Attach caller-owned tables to the handle (borrowed until detach/destroy).
+ * For B2W_MODE_PRECOMP_FIRST_ORDER pass d_alias_indptr = NULL. */
+int b2w_graph_set_alias(b2w_graph* g, const uint64_t* d_alias_indptr, const uint32_t* d_alias_j,
+                        const float* d_alias_q);
+
+/* ---- the walk kernel -------------------------------------------------------------------
+ * Replaces Base._random_walks (pecanpy.py:164-210) together with the move_forward closure of
+ * `mode`.  Walks rows [row0, row0 + n_rows) of the caller's (host-shuffled, pecanpy.py:135-141)
+ * start array: d_start[i] is the start node of global row row0 + i, and row i of d_out
+ * (uint32, leading dimension ld_out >= walk_length + 2) receives
+ *     [start, step 1, ..., step L, 0-padding ..., effective_length]
+ * exactly as the reference's matrix (pecanpy.py:182-206): column L+1 holds the number of valid
+ * node entries (L+1, or 1 for an isolated start, or j when the walker is stuck before step j).
+ * The kernel writes every element of the row; d_out needs no initialisation.
+ * p, q: return / in-out parameters; extend: node2vec+ (requires d_thr, f32[n]).
+ * seed: Philox key (B2W_RNG_PHILOX); d_feed: uniforms (B2W_RNG_FEED).
+ * d_work/work_bytes: scratch of at least b2w_walk_work_bytes(g, mode) bytes (may be 0/NULL
+ * when that returns 0).  d_stats: optional device pointer to a b2w_walk_stats that the kernel
+ * ADDS to (zero it first), or NULL. */
+size_t b2w_walk_work_bytes(const b2w_graph* g, int mode);
+int b2w_walk(const b2w_graph* g, int mode, double p, double q, int extend, const float* d_thr,
+             const uint32_t* d_start, uint64_t row0, uint64_t n_rows, uint32_t walk_length,
+             uint64_t seed, int rng_mode, const double* d_feed, uint32_t* d_out, uint64_t ld_out,
+             void* d_work, size_t work_bytes, b2w_walk_stats* d_stats, uint32_t flags, void* stream);
+
+/* Host-buffer convenience wrapper (the end-to-end call): copies h_start to the device in
+ * batches, walks, and copies the rows back into h_out [n_rows, walk_length + 2]; H2D, kernel and
+ * D2H of consecutive batches overlap on internal streams.  Pinned host buffers are used
+ * directly; pageable buffers work but copy slower.  Synchronous.  h_stats may be NULL. */
+int b2w_walk_host(const b2w_graph* g, int mode, double p, double q, int extend, const float* d_thr,
+                  const uint32_t* h_start, uint64_t row0, uint64_t n_rows, uint32_t walk_length,
+                  uint64_t seed, uint32_t* h_out, uint64_t batch_rows, b2w_walk_stats* h_stats,
+                  uint32_t flags);
+
+/* Sum of (effective_length - 1) over the rows of a device walk matrix (the metric's unit). */
+int b2w_count_steps(const uint32_t* d_out, uint64_t n_rows, uint32_t walk_length, uint64_t ld_out,
+                    uint64_t* d_steps /* device u64, overwritten */, void* stream);
+
+/* Philox4x32-10 of one counter/key on the device (known-answer self test). */
+int b2w_philox_selftest(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2W_H_ */

@@ -1,0 +1,85 @@
+"""ctypes binding of libb2w.so (include/b2w.h).  Thin by design: argument marshalling only.
+
+The CUDA library is the product; if it is missing this module raises -- there is no CPU
+fallback anywhere in the package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libb2w.so")
+
+OK = 0
+MODE_SPARSE_OTF, MODE_PRECOMP, MODE_DENSE_OTF, MODE_FIRST_ORDER_UNWEIGHTED, MODE_PRECOMP_FIRST_ORDER = range(5)
+RNG_PHILOX, RNG_FEED = 0, 1
+FLAG_FORCE_EXACT_REPLAY = 0x1
+FLAG_NO_FILTER_STATS = 0x2
+FLAG_THREAD_PER_WALKER = 0x4
+GRAPH_CSR, GRAPH_DENSE, GRAPH_UNWEIGHTED, GRAPH_HAS_ALIAS = 0x1, 0x2, 0x4, 0x8
+
+EXPORTS = [
+    "b2w_version", "b2w_last_error", "b2w_device_count", "b2w_graph_csr_create", "b2w_graph_dense_create",
+    "b2w_graph_info_get", "b2w_graph_destroy", "b2w_alias_build_work_bytes", "b2w_alias_build",
+    "b2w_alias_build_first_order", "b2w_graph_set_alias", "b2w_walk_work_bytes", "b2w_walk", "b2w_walk_host",
+    "b2w_count_steps", "b2w_philox_selftest",
+]
+
+
+class GraphInfo(C.Structure):
+    _fields_ = [("num_nodes", C.c_uint32), ("nnz", C.c_uint64), ("max_degree", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class WalkStats(C.Structure):
+    _fields_ = [("steps", C.c_uint64), ("exact_replays", C.c_uint64), ("seq_sums", C.c_uint64),
+                ("overflow_choices", C.c_uint64)]
+
+
+class B2WError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load libb2w.so; raise loudly (never fall back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the CUDA extension has not been built. Run "
+            "`python -m pecanpy_b200.build` (needs nvcc; cross-compiles for sm_100a without a GPU).")
+    L = C.CDLL(LIB_PATH)
+    vp, u32, u64, i32, dbl, sz = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int, C.c_double, C.c_size_t
+    L.b2w_version.restype = i32
+    L.b2w_last_error.restype = C.c_char_p
+    L.b2w_device_count.argtypes = [C.POINTER(i32)]
+    L.b2w_graph_csr_create.argtypes = [i32, u32, u64, vp, vp, vp, C.POINTER(vp)]
+    L.b2w_graph_dense_create.argtypes = [i32, u32, vp, vp, C.POINTER(vp)]
+    L.b2w_graph_info_get.argtypes = [vp, C.POINTER(GraphInfo)]
+    L.b2w_graph_destroy.argtypes = [vp]
+    L.b2w_graph_destroy.restype = None
+    L.b2w_alias_build_work_bytes.argtypes = [vp]
+    L.b2w_alias_build_work_bytes.restype = sz
+    L.b2w_alias_build.argtypes = [vp, dbl, dbl, i32, vp, vp, vp, vp, vp, sz, vp]
+    L.b2w_alias_build_first_order.argtypes = [vp, vp, vp, vp, sz, vp]
+    L.b2w_graph_set_alias.argtypes = [vp, vp, vp, vp]
+    L.b2w_walk_work_bytes.argtypes = [vp, i32]
+    L.b2w_walk_work_bytes.restype = sz
+    L.b2w_walk.argtypes = [vp, i32, dbl, dbl, i32, vp, vp, u64, u64, u32, u64, i32, vp, vp, u64, vp, sz, vp, u32, vp]
+    L.b2w_walk_host.argtypes = [vp, i32, dbl, dbl, i32, vp, vp, u64, u64, u32, u64, vp, u64, C.POINTER(WalkStats), u32]
+    L.b2w_count_steps.argtypes = [vp, u64, u32, u64, vp, vp]
+    L.b2w_philox_selftest.argtypes = [C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
+    for name in EXPORTS:
+        getattr(L, name)   # AttributeError here == the library does not export what b2w.h declares
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str = ""):
+    if rc != OK:
+        msg = lib().b2w_last_error().decode("utf-8", "replace")
+        raise B2WError(f"{what or 'libb2w'} failed ({rc}): {msg}")

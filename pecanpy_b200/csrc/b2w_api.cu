@@ -1,0 +1,348 @@
+// b2w_api.cu -- the C ABI of libb2w.so (see include/b2w.h): handles, validation, dispatch.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "b2w_common.cuh"
+
+// ---------------------------------------------------------------- errors
+static thread_local char g_err[512] = "";
+
+void b2w_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+int b2w_cuda_fail(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return B2W_OK;
+  b2w_set_error("CUDA error in %s: %s", what, cudaGetErrorString(e));
+  return B2W_ERR_CUDA;
+}
+
+extern "C" int b2w_version(void) { return B2W_VERSION; }
+extern "C" const char* b2w_last_error(void) { return g_err; }
+extern "C" int b2w_device_count(int* out) {
+  if (!out) { b2w_set_error("b2w_device_count: null out"); return B2W_ERR_INVALID; }
+  B2W_CUDA(cudaGetDeviceCount(out));
+  return B2W_OK;
+}
+
+// ---------------------------------------------------------------- validation kernels
+struct CheckResult {
+  unsigned int bad_indptr, bad_order, bad_index, bad_weight, not_unweighted, max_degree;
+};
+
+__global__ void csr_check_kernel(uint32_t n, uint64_t nnz, const uint32_t* __restrict__ indptr,
+                                 const uint32_t* __restrict__ indices, const float* __restrict__ data,
+                                 CheckResult* res) {
+  unsigned int bad_indptr = 0, bad_order = 0, bad_index = 0, bad_weight = 0, notuw = 0, maxdeg = 0;
+  for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t s = indptr[r], e = indptr[r + 1];
+    if (e < s || e > nnz) { bad_indptr = 1; continue; }
+    if (r == 0 && s != 0) bad_indptr = 1;
+    if (r == n - 1 && e != nnz) bad_indptr = 1;
+    maxdeg = max(maxdeg, e - s);
+    uint32_t last = 0;
+    for (uint32_t k = s; k < e; ++k) {
+      uint32_t x = indices[k];
+      float w = data[k];
+      if (x >= n) bad_index = 1;
+      if (k > s && x <= last) bad_order = 1;                           // rows sorted ascending, no duplicates
+      if (!(w >= 0.f) || !(w < INFINITY)) bad_weight = 1;              // NaN, negative, inf
+      if (w != 1.0f) notuw = 1;
+      last = x;
+    }
+  }
+  if (bad_indptr) atomicOr(&res->bad_indptr, 1u);
+  if (bad_order) atomicOr(&res->bad_order, 1u);
+  if (bad_index) atomicOr(&res->bad_index, 1u);
+  if (bad_weight) atomicOr(&res->bad_weight, 1u);
+  if (notuw) atomicOr(&res->not_unweighted, 1u);
+  atomicMax(&res->max_degree, maxdeg);
+}
+
+__global__ void dense_check_kernel(uint64_t total, const double* __restrict__ data, const uint8_t* __restrict__ nz,
+                                   CheckResult* res) {
+  unsigned int bad_weight = 0, bad_mask = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    double w = data[i];
+    if (!(w >= 0.0) || !(w < (double)INFINITY)) bad_weight = 1;
+    if ((w != 0.0) != (nz[i] != 0)) bad_mask = 1;                      // graph.py:580
+  }
+  if (bad_weight) atomicOr(&res->bad_weight, 1u);
+  if (bad_mask) atomicOr(&res->bad_order, 1u);
+}
+
+static int new_handle(int device, b2w_graph** out, b2w_graph** gp) {
+  if (!out) { b2w_set_error("graph create: null out"); return B2W_ERR_INVALID; }
+  *out = nullptr;
+  B2W_CUDA(cudaSetDevice(device));
+  b2w_graph* g = new (std::nothrow) b2w_graph();
+  if (!g) { b2w_set_error("graph create: out of host memory"); return B2W_ERR_NOMEM; }
+  memset(g, 0, sizeof *g);
+  g->device = device;
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { delete g; return b2w_cuda_fail(e, "cudaGetDeviceProperties"); }
+  g->num_sms = prop.multiProcessorCount;
+  *gp = g;
+  return B2W_OK;
+}
+
+static int run_check(CheckResult* h, void (*launch)(CheckResult*, void*), void* ctx) {
+  CheckResult* d = nullptr;
+  B2W_CUDA(cudaMalloc(&d, sizeof(CheckResult)));
+  cudaError_t e = cudaMemset(d, 0, sizeof(CheckResult));
+  if (e == cudaSuccess) { launch(d, ctx); e = cudaGetLastError(); }
+  if (e == cudaSuccess) e = cudaMemcpy(h, d, sizeof(CheckResult), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return b2w_cuda_fail(e, "graph validation");
+}
+
+extern "C" int b2w_graph_csr_create(int device, uint32_t n, uint64_t nnz, const uint32_t* d_indptr,
+                                    const uint32_t* d_indices, const float* d_data, b2w_graph** out) {
+  if (!d_indptr || (nnz && (!d_indices || !d_data))) { b2w_set_error("csr create: null array"); return B2W_ERR_INVALID; }
+  if (n == 0) { b2w_set_error("csr create: empty graph"); return B2W_ERR_INVALID; }
+  if (nnz >= 0xFFFFFFFFull) { b2w_set_error("csr create: nnz must fit uint32 (reference indptr is uint32, graph.py:325)"); return B2W_ERR_INVALID; }
+  b2w_graph* g = nullptr;
+  int rc = new_handle(device, out, &g);
+  if (rc) return rc;
+  g->n = n; g->nnz = nnz; g->indptr = d_indptr; g->indices = d_indices; g->data = d_data;
+  g->flags = B2W_GRAPH_CSR;
+  struct Ctx { uint32_t n; uint64_t nnz; const uint32_t* ip; const uint32_t* ix; const float* dt; int sms; } ctx{n, nnz, d_indptr, d_indices, d_data, g->num_sms};
+  CheckResult h{};
+  rc = run_check(&h, [](CheckResult* d, void* c) {
+    Ctx* x = (Ctx*)c;
+    csr_check_kernel<<<x->sms * 8, 256>>>(x->n, x->nnz, x->ip, x->ix, x->dt, d);
+  }, &ctx);
+  if (rc) { delete g; return rc; }
+  if (h.bad_indptr || h.bad_order || h.bad_index || h.bad_weight) {
+    b2w_set_error("csr create: invalid graph (%s%s%s%s)", h.bad_indptr ? "indptr not monotone / inconsistent with nnz; " : "",
+                  h.bad_order ? "a row is not sorted ascending and duplicate-free; " : "",
+                  h.bad_index ? "column index out of range; " : "", h.bad_weight ? "negative, NaN or infinite weight" : "");
+    delete g;
+    return B2W_ERR_GRAPH;
+  }
+  g->max_degree = h.max_degree;
+  if (!h.not_unweighted) g->flags |= B2W_GRAPH_UNWEIGHTED;
+  *out = g;
+  return B2W_OK;
+}
+
+extern "C" int b2w_graph_dense_create(int device, uint32_t n, const double* d_data, const uint8_t* d_nonzero,
+                                      b2w_graph** out) {
+  if (!d_data || !d_nonzero || n == 0) { b2w_set_error("dense create: null array / empty graph"); return B2W_ERR_INVALID; }
+  b2w_graph* g = nullptr;
+  int rc = new_handle(device, out, &g);
+  if (rc) return rc;
+  g->n = n; g->nnz = 0; g->dense = d_data; g->nonzero = d_nonzero; g->flags = B2W_GRAPH_DENSE; g->max_degree = n;
+  struct Ctx { uint64_t total; const double* d; const uint8_t* z; int sms; } ctx{(uint64_t)n * n, d_data, d_nonzero, g->num_sms};
+  CheckResult h{};
+  rc = run_check(&h, [](CheckResult* d, void* c) {
+    Ctx* x = (Ctx*)c;
+    dense_check_kernel<<<x->sms * 16, 256>>>(x->total, x->d, x->z, d);
+  }, &ctx);
+  if (rc) { delete g; return rc; }
+  if (h.bad_weight || h.bad_order) {
+    b2w_set_error("dense create: invalid graph (%s%s)", h.bad_weight ? "negative, NaN or infinite weight; " : "",
+                  h.bad_order ? "nonzero mask != (data != 0)" : "");
+    delete g;
+    return B2W_ERR_GRAPH;
+  }
+  *out = g;
+  return B2W_OK;
+}
+
+extern "C" int b2w_graph_info_get(const b2w_graph* g, b2w_graph_info* out) {
+  if (!g || !out) { b2w_set_error("graph info: null argument"); return B2W_ERR_INVALID; }
+  out->num_nodes = g->n; out->nnz = g->nnz; out->max_degree = g->max_degree; out->flags = g->flags;
+  return B2W_OK;
+}
+
+extern "C" void b2w_graph_destroy(b2w_graph* g) { delete g; }
+
+extern "C" int b2w_graph_set_alias(b2w_graph* g, const uint64_t* aip, const uint32_t* aj, const float* aq) {
+  if (!g || !(g->flags & B2W_GRAPH_CSR)) { b2w_set_error("set_alias: CSR graph handle required"); return B2W_ERR_INVALID; }
+  g->alias_indptr = aip; g->alias_j = aj; g->alias_q = aq;
+  if (aj && aq) g->flags |= B2W_GRAPH_HAS_ALIAS; else g->flags &= ~B2W_GRAPH_HAS_ALIAS;
+  return B2W_OK;
+}
+
+// ---------------------------------------------------------------- walk dispatch
+static bool is_pow2(double v, float* inv) {
+  int e;
+  double m = frexp(v, &e);
+  if (m == 0.5 && e > -60 && e < 60) { *inv = (float)(1.0 / v); return true; }
+  *inv = 0.f;
+  return false;
+}
+
+void b2w_fill_bias_params(WalkParams& P, double p, double q) {
+  P.p = p; P.q = q;
+  P.invq = 1.0 / q;
+  P.supp = P.invq < 1.0 ? P.invq : 1.0;
+  P.p_pow2 = is_pow2(p, &P.invp_f);
+  P.q_pow2 = is_pow2(q, &P.invq_f);
+}
+
+extern "C" size_t b2w_walk_work_bytes(const b2w_graph* g, int mode) {
+  if (!g) return 0;
+  if (mode == B2W_MODE_SPARSE_OTF && (g->flags & B2W_GRAPH_CSR)) return b2w_sparse_warp_work_bytes(g);
+  if (mode == B2W_MODE_DENSE_OTF) return 256;
+  return 0;
+}
+
+extern "C" int b2w_walk(const b2w_graph* g, int mode, double p, double q, int extend, const float* d_thr,
+                        const uint32_t* d_start, uint64_t row0, uint64_t n_rows, uint32_t walk_length,
+                        uint64_t seed, int rng_mode, const double* d_feed, uint32_t* d_out, uint64_t ld_out,
+                        void* d_work, size_t work_bytes, b2w_walk_stats* d_stats, uint32_t flags, void* stream) {
+  if (!g) { b2w_set_error("b2w_walk: null graph"); return B2W_ERR_INVALID; }
+  if (n_rows == 0) return B2W_OK;
+  if (!d_start || !d_out) { b2w_set_error("b2w_walk: null start/out"); return B2W_ERR_INVALID; }
+  if (walk_length < 1 || walk_length > (1u << 24)) { b2w_set_error("b2w_walk: walk_length out of range"); return B2W_ERR_INVALID; }
+  if (ld_out < (uint64_t)walk_length + 2) { b2w_set_error("b2w_walk: ld_out < walk_length + 2"); return B2W_ERR_INVALID; }
+  if (!(p > 0.0) || !(q > 0.0) || !std::isfinite(p) || !std::isfinite(q)) { b2w_set_error("b2w_walk: p and q must be finite and > 0"); return B2W_ERR_INVALID; }
+  if (rng_mode != B2W_RNG_PHILOX && rng_mode != B2W_RNG_FEED) { b2w_set_error("b2w_walk: bad rng_mode"); return B2W_ERR_INVALID; }
+  if (rng_mode == B2W_RNG_FEED && !d_feed) { b2w_set_error("b2w_walk: B2W_RNG_FEED needs d_feed"); return B2W_ERR_INVALID; }
+  const bool dense = mode == B2W_MODE_DENSE_OTF;
+  if (dense != ((g->flags & B2W_GRAPH_DENSE) != 0)) { b2w_set_error("b2w_walk: mode %d does not match the graph layout", mode); return B2W_ERR_INVALID; }
+  if (mode < 0 || mode > B2W_MODE_PRECOMP_FIRST_ORDER) { b2w_set_error("b2w_walk: unknown mode %d", mode); return B2W_ERR_INVALID; }
+  if (rng_mode == B2W_RNG_FEED && mode != B2W_MODE_SPARSE_OTF && mode != B2W_MODE_DENSE_OTF) {
+    b2w_set_error("b2w_walk: B2W_RNG_FEED is defined for the OTF modes only (draw counts are data dependent otherwise)");
+    return B2W_ERR_UNSUPPORTED;
+  }
+  if ((mode == B2W_MODE_PRECOMP || mode == B2W_MODE_PRECOMP_FIRST_ORDER) &&
+      (!(g->flags & B2W_GRAPH_HAS_ALIAS) || (mode == B2W_MODE_PRECOMP && !g->alias_indptr))) {
+    b2w_set_error("b2w_walk: alias tables not attached (b2w_graph_set_alias)");
+    return B2W_ERR_INVALID;
+  }
+  const bool ext = extend != 0 && (mode == B2W_MODE_SPARSE_OTF || mode == B2W_MODE_DENSE_OTF);
+  if (ext && !d_thr) { b2w_set_error("b2w_walk: extend requires noise thresholds"); return B2W_ERR_INVALID; }
+  if ((mode == B2W_MODE_FIRST_ORDER_UNWEIGHTED || mode == B2W_MODE_PRECOMP_FIRST_ORDER) && (p != 1.0 || q != 1.0)) {
+    b2w_set_error("b2w_walk: first-order modes require p == q == 1 (cli.py:179-197)");
+    return B2W_ERR_INVALID;
+  }
+  const bool warp_kernel = mode == B2W_MODE_SPARSE_OTF && !(flags & B2W_FLAG_THREAD_PER_WALKER);
+  size_t need = (warp_kernel || dense) ? b2w_walk_work_bytes(g, mode) : 0;
+  if (need && (!d_work || work_bytes < need)) {
+    b2w_set_error("b2w_walk: scratch too small (%zu < %zu bytes)", work_bytes, need);
+    return B2W_ERR_INVALID;
+  }
+  B2W_CUDA(cudaSetDevice(g->device));
+  WalkParams P{};
+  P.n = g->n; P.indptr = g->indptr; P.indices = g->indices; P.data = g->data;
+  P.dense = g->dense; P.nonzero = g->nonzero; P.thr = d_thr;
+  P.alias_indptr = g->alias_indptr; P.alias_j = g->alias_j; P.alias_q = g->alias_q;
+  P.start = d_start; P.feed = d_feed; P.out = d_out; P.ld_out = ld_out;
+  P.row0 = row0; P.n_rows = n_rows; P.L = walk_length;
+  P.key0 = (uint32_t)seed; P.key1 = (uint32_t)(seed >> 32);
+  P.rng_mode = rng_mode; P.extend = ext ? 1 : 0;
+  b2w_fill_bias_params(P, p, q);
+  P.flags = flags; P.work = (float*)d_work; P.stats = d_stats;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dense) return b2w_launch_dense(g, ext, P, s);
+  if (warp_kernel) return b2w_launch_sparse_warp(g, P, s);
+  return b2w_launch_thread_walk(g, mode, ext, P, s);
+}
+
+// ---------------------------------------------------------------- host-buffer wrapper
+extern "C" int b2w_walk_host(const b2w_graph* g, int mode, double p, double q, int extend, const float* d_thr,
+                             const uint32_t* h_start, uint64_t row0, uint64_t n_rows, uint32_t L, uint64_t seed,
+                             uint32_t* h_out, uint64_t batch_rows, b2w_walk_stats* h_stats, uint32_t flags) {
+  if (!g) { b2w_set_error("b2w_walk_host: null graph"); return B2W_ERR_INVALID; }
+  if (n_rows == 0) return B2W_OK;
+  if (!h_start || !h_out) { b2w_set_error("b2w_walk_host: null start/out"); return B2W_ERR_INVALID; }
+  B2W_CUDA(cudaSetDevice(g->device));
+  if (batch_rows == 0) batch_rows = 1u << 20;
+  if (batch_rows > n_rows) batch_rows = n_rows;
+  const uint64_t ld = (uint64_t)L + 2;
+  const size_t wb = b2w_walk_work_bytes(g, mode);
+  constexpr int NS = 2;
+  cudaStream_t st[NS] = {nullptr, nullptr};
+  uint32_t* d_start[NS] = {nullptr, nullptr};
+  uint32_t* d_out[NS] = {nullptr, nullptr};
+  void* d_work[NS] = {nullptr, nullptr};
+  b2w_walk_stats* d_stats = nullptr;
+  int rc = B2W_OK;
+  cudaError_t e = cudaSuccess;
+  for (int k = 0; k < NS && e == cudaSuccess; ++k) {
+    e = cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&d_start[k], batch_rows * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&d_out[k], batch_rows * ld * sizeof(uint32_t));
+    if (e == cudaSuccess && wb) e = cudaMalloc(&d_work[k], wb);
+  }
+  if (e == cudaSuccess) e = cudaMalloc(&d_stats, sizeof(b2w_walk_stats));
+  if (e == cudaSuccess) e = cudaMemset(d_stats, 0, sizeof(b2w_walk_stats));
+  if (e != cudaSuccess) rc = b2w_cuda_fail(e, "b2w_walk_host setup");
+  uint64_t done = 0;
+  for (int b = 0; rc == B2W_OK && done < n_rows; ++b) {
+    const int k = b % NS;
+    const uint64_t rows = (n_rows - done < batch_rows) ? (n_rows - done) : batch_rows;
+    // the stream serialises reuse of this slot's buffers with its previous batch
+    e = cudaMemcpyAsync(d_start[k], h_start + done, rows * sizeof(uint32_t), cudaMemcpyHostToDevice, st[k]);
+    if (e != cudaSuccess) { rc = b2w_cuda_fail(e, "H2D start"); break; }
+    rc = b2w_walk(g, mode, p, q, extend, d_thr, d_start[k], row0 + done, rows, L, seed, B2W_RNG_PHILOX, nullptr,
+                  d_out[k], ld, d_work[k], wb, d_stats, flags, st[k]);
+    if (rc) break;
+    e = cudaMemcpyAsync(h_out + done * ld, d_out[k], rows * ld * sizeof(uint32_t), cudaMemcpyDeviceToHost, st[k]);
+    if (e != cudaSuccess) { rc = b2w_cuda_fail(e, "D2H walks"); break; }
+    done += rows;
+  }
+  for (int k = 0; k < NS; ++k)
+    if (st[k]) { e = cudaStreamSynchronize(st[k]); if (e != cudaSuccess && rc == B2W_OK) rc = b2w_cuda_fail(e, "b2w_walk_host sync"); }
+  if (rc == B2W_OK && h_stats) {
+    e = cudaMemcpy(h_stats, d_stats, sizeof(b2w_walk_stats), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = b2w_cuda_fail(e, "stats D2H");
+  }
+  for (int k = 0; k < NS; ++k) {
+    if (d_start[k]) cudaFree(d_start[k]);
+    if (d_out[k]) cudaFree(d_out[k]);
+    if (d_work[k]) cudaFree(d_work[k]);
+    if (st[k]) cudaStreamDestroy(st[k]);
+  }
+  if (d_stats) cudaFree(d_stats);
+  return rc;
+}
+
+// ---------------------------------------------------------------- helpers
+__global__ void count_steps_kernel(const uint32_t* __restrict__ out, uint64_t n_rows, uint32_t L, uint64_t ld,
+                                   unsigned long long* steps) {
+  unsigned long long acc = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_rows; i += (uint64_t)gridDim.x * blockDim.x)
+    acc += out[i * ld + L + 1] - 1u;
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(B2W_FULL, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(steps, acc);
+}
+
+extern "C" int b2w_count_steps(const uint32_t* d_out, uint64_t n_rows, uint32_t L, uint64_t ld_out, uint64_t* d_steps,
+                               void* stream) {
+  if (!d_out || !d_steps) { b2w_set_error("b2w_count_steps: null pointer"); return B2W_ERR_INVALID; }
+  cudaStream_t s = (cudaStream_t)stream;
+  B2W_CUDA(cudaMemsetAsync(d_steps, 0, 8, s));
+  if (n_rows == 0) return B2W_OK;
+  uint64_t blocks = (n_rows + 255) / 256;
+  if (blocks > 2048) blocks = 2048;
+  count_steps_kernel<<<(unsigned)blocks, 256, 0, s>>>(d_out, n_rows, L, ld_out, (unsigned long long*)d_steps);
+  return b2w_cuda_fail(cudaGetLastError(), "count_steps_kernel launch");
+}
+
+__global__ void philox_selftest_kernel(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+  uint32_t o[4];
+  philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], o);
+  out[0] = o[0]; out[1] = o[1]; out[2] = o[2]; out[3] = o[3];
+}
+
+extern "C" int b2w_philox_selftest(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t* d = nullptr;
+  B2W_CUDA(cudaMalloc(&d, 10 * sizeof(uint32_t)));
+  cudaError_t e = cudaMemcpy(d, ctr, 16, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d + 4, key, 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) { philox_selftest_kernel<<<1, 1>>>(d, d + 4, d + 6); e = cudaGetLastError(); }
+  if (e == cudaSuccess) e = cudaMemcpy(out, d + 6, 16, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  return b2w_cuda_fail(e, "philox selftest");
+}

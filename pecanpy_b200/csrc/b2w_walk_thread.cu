@@ -1,0 +1,113 @@
+// b2w_walk_thread.cu -- lane-per-walker kernels.
+//
+// PreComp (alias draw), the two first-order modes, and a lane-per-walker SparseOTF variant.
+// One thread owns one walker for its whole life: per step the work is a handful of dependent
+// gathers (binary search of prev in cur's row, alias_q/alias_j, indices), so the natural
+// mapping is one lane per walker with 32 independent gather chains in flight per warp.
+// Reference: pecanpy.py:164-210 (_random_walks), :409-438 (PreComp.move_forward),
+// :304-307 (FirstOrderUnweighted), :327-332 (PreCompFirstOrder), :668-677 (alias_draw).
+#include "b2w_probs.cuh"
+
+namespace {
+
+// alias_draw (pecanpy.py:668-677): kk = randint(k); rand() < q[kk] ? kk : j[kk]
+__device__ __forceinline__ uint32_t alias_draw(const uint32_t* __restrict__ j, const float* __restrict__ q,
+                                               uint64_t off, uint32_t k, StepRng& rng) {
+  uint32_t kk = rng.randint(k);
+  double u = rng.uniform();
+  float qv = q[off + kk];
+  return (u < (double)qv) ? kk : j[off + kk];
+}
+
+template <int MODE, bool EXTEND>
+__global__ void __launch_bounds__(256) walk_thread_kernel(const WalkParams P) {
+  const uint32_t L = P.L;
+  uint64_t steps = 0, overflow = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < P.n_rows;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    uint32_t* out = P.out + i * P.ld_out;
+    const uint64_t row = P.row0 + i;
+    uint32_t cur = P.start[i];
+    uint32_t prev = 0;
+    uint32_t eff = L + 1;
+    out[0] = cur;
+    uint32_t j = 1;
+    for (; j <= L; ++j) {
+      uint32_t cs = P.indptr[cur];
+      uint32_t deg = P.indptr[cur + 1] - cs;
+      if (deg == 0) { eff = j; break; }                                // pecanpy.py:194-196,204-206
+      uint32_t choice;
+      if (MODE == B2W_MODE_SPARSE_OTF) {
+        double u = step_uniform(P, i, j);
+        choice = otf_choice_seq<EXTEND>(P, cur, j > 1, prev, u);
+        if (choice == deg) ++overflow;
+      } else {
+        StepRng rng;
+        rng.begin(P.key0, P.key1, row, j);
+        if (MODE == B2W_MODE_PRECOMP) {
+          if (j == 1) {
+            // first step: cumsum/searchsorted on the NON-extended first-order probs (:412-424)
+            choice = otf_choice_seq<false>(P, cur, false, 0, rng.uniform());
+            if (choice == deg) ++overflow;
+          } else {
+            // np.searchsorted(indices[start:end], prev) (:429); table at alias_indptr + deg*idx (:433-434)
+            uint32_t lo = 0, hi = deg;
+            while (lo < hi) {
+              uint32_t mid = (lo + hi) >> 1;
+              if (P.indices[cs + mid] < prev) lo = mid + 1; else hi = mid;
+            }
+            uint64_t off = P.alias_indptr[cur] + (uint64_t)deg * lo;
+            choice = alias_draw(P.alias_j, P.alias_q, off, deg, rng);
+          }
+        } else if (MODE == B2W_MODE_FIRST_ORDER_UNWEIGHTED) {
+          choice = rng.randint(deg);                                   // randint(start, end) (:306-307)
+        } else {                                                       // PRECOMP_FIRST_ORDER (:329-332)
+          choice = alias_draw(P.alias_j, P.alias_q, cs, deg, rng);
+        }
+      }
+      uint32_t nxt = P.indices[cs + choice];
+      out[j] = nxt;
+      prev = cur;
+      cur = nxt;
+      ++steps;
+    }
+    for (uint32_t z = j; z <= L; ++z) out[z] = 0;                      // zero tail (np.zeros, :182)
+    out[L + 1] = eff;
+  }
+  if (P.stats && !(P.flags & B2W_FLAG_NO_FILTER_STATS)) {
+    // one atomic per warp
+    for (int o = 16; o; o >>= 1) {
+      steps += __shfl_xor_sync(B2W_FULL, steps, o);
+      overflow += __shfl_xor_sync(B2W_FULL, overflow, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd((unsigned long long*)&P.stats->steps, (unsigned long long)steps);
+      if (overflow) atomicAdd((unsigned long long*)&P.stats->overflow_choices, (unsigned long long)overflow);
+    }
+  }
+}
+
+template <int MODE, bool EXTEND>
+int launch(const b2w_graph* g, const WalkParams& P, cudaStream_t s) {
+  int threads = 256;
+  uint64_t want = (P.n_rows + threads - 1) / threads;
+  uint64_t cap = (uint64_t)g->num_sms * 8 * 4;   // grid-stride beyond a few waves
+  int blocks = (int)(want < cap ? want : cap);
+  if (blocks < 1) blocks = 1;
+  walk_thread_kernel<MODE, EXTEND><<<blocks, threads, 0, s>>>(P);
+  return b2w_cuda_fail(cudaGetLastError(), "walk_thread_kernel launch");
+}
+
+}  // namespace
+
+int b2w_launch_thread_walk(const b2w_graph* g, int mode, int extend, const WalkParams& P, cudaStream_t s) {
+  switch (mode) {
+    case B2W_MODE_SPARSE_OTF:
+      return extend ? launch<B2W_MODE_SPARSE_OTF, true>(g, P, s) : launch<B2W_MODE_SPARSE_OTF, false>(g, P, s);
+    case B2W_MODE_PRECOMP: return launch<B2W_MODE_PRECOMP, false>(g, P, s);
+    case B2W_MODE_FIRST_ORDER_UNWEIGHTED: return launch<B2W_MODE_FIRST_ORDER_UNWEIGHTED, false>(g, P, s);
+    case B2W_MODE_PRECOMP_FIRST_ORDER: return launch<B2W_MODE_PRECOMP_FIRST_ORDER, false>(g, P, s);
+  }
+  b2w_set_error("b2w_launch_thread_walk: unsupported mode %d", mode);
+  return B2W_ERR_UNSUPPORTED;
+}

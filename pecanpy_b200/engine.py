@@ -1,0 +1,254 @@
+"""Device-side glue: torch tensors as device buffers, libb2w.so for every kernel.
+
+PyTorch is plumbing here (allocation, streams, ``torch.distributed``); all computation is in
+the hand-written CUDA library behind ``include/b2w.h``.  There is no CPU code path: without a
+CUDA device or without the built extension every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _capi as capi
+
+MODES = {
+    "SparseOTF": capi.MODE_SPARSE_OTF,
+    "PreComp": capi.MODE_PRECOMP,
+    "DenseOTF": capi.MODE_DENSE_OTF,
+    "FirstOrderUnweighted": capi.MODE_FIRST_ORDER_UNWEIGHTED,
+    "PreCompFirstOrder": capi.MODE_PRECOMP_FIRST_ORDER,
+}
+
+
+def _require_cuda(device) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("pecanpy_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise ValueError(f"CUDA device required, got {dev}")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def _to_dev(arr: np.ndarray, dev: torch.device, view_dtype=None) -> torch.Tensor:
+    a = np.ascontiguousarray(arr)
+    if view_dtype is not None:
+        a = a.view(view_dtype)
+    return torch.from_numpy(a).to(dev, non_blocking=False)
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class WalkEngine:
+    """One graph resident on one GPU + the kernels that walk it."""
+
+    def __init__(self, device=None):
+        self.lib = capi.lib()
+        self.device = _require_cuda(device)
+        self.handle = C.c_void_p(None)
+        self.kind = None
+        self.n = 0
+        self._keep = {}          # device tensors borrowed by the handle
+        self.thr: Optional[torch.Tensor] = None
+        self._work: dict = {}
+        self.alias: Optional[Tuple[np.ndarray, torch.Tensor, torch.Tensor]] = None
+        self.last_stats = None
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def from_csr(cls, indptr, indices, data, device=None) -> "WalkEngine":
+        e = cls(device)
+        indptr = np.ascontiguousarray(indptr, dtype=np.uint32)
+        indices = np.ascontiguousarray(indices, dtype=np.uint32)
+        data = np.ascontiguousarray(data, dtype=np.float32)
+        n, nnz = indptr.size - 1, int(indptr[-1])
+        if indices.size != nnz or data.size != nnz:
+            raise ValueError("CSR arrays are inconsistent: indptr[-1] != len(indices) / len(data)")
+        padded = np.zeros(nnz + 1, dtype=np.uint32)       # one element for the unchecked choice == deg read
+        padded[:nnz] = indices
+        with torch.cuda.device(e.device):
+            e._keep["indptr"] = _to_dev(indptr, e.device, np.int32)
+            e._keep["indices"] = _to_dev(padded, e.device, np.int32)
+            e._keep["data"] = _to_dev(data if nnz else np.zeros(1, np.float32), e.device)
+            h = C.c_void_p(None)
+            capi.check(e.lib.b2w_graph_csr_create(e.device.index, n, nnz, _ptr(e._keep["indptr"]),
+                                                  _ptr(e._keep["indices"]), _ptr(e._keep["data"]), C.byref(h)),
+                       "b2w_graph_csr_create")
+        e.handle, e.kind, e.n = h, "csr", n
+        return e
+
+    @classmethod
+    def from_dense(cls, data, nonzero, device=None) -> "WalkEngine":
+        e = cls(device)
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        nz = np.ascontiguousarray(nonzero).view(np.uint8)
+        if data.ndim != 2 or data.shape[0] != data.shape[1] or nz.shape != data.shape:
+            raise ValueError("dense graph: data must be square and nonzero must have the same shape")
+        n = data.shape[0]
+        with torch.cuda.device(e.device):
+            e._keep["dense"] = _to_dev(data, e.device)
+            e._keep["nonzero"] = _to_dev(nz, e.device)
+            h = C.c_void_p(None)
+            capi.check(e.lib.b2w_graph_dense_create(e.device.index, n, _ptr(e._keep["dense"]),
+                                                    _ptr(e._keep["nonzero"]), C.byref(h)), "b2w_graph_dense_create")
+        e.handle, e.kind, e.n = h, "dense", n
+        return e
+
+    def close(self):
+        if getattr(self, "handle", None) is not None and self.handle:
+            self.lib.b2w_graph_destroy(self.handle)
+            self.handle = C.c_void_p(None)
+        self._keep.clear()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> capi.GraphInfo:
+        gi = capi.GraphInfo()
+        capi.check(self.lib.b2w_graph_info_get(self.handle, C.byref(gi)), "b2w_graph_info_get")
+        return gi
+
+    def set_thresholds(self, thr: Optional[np.ndarray]):
+        """node2vec+ noise thresholds (float32[n], computed on the host as in the reference)."""
+        self.thr = None if thr is None else _to_dev(np.ascontiguousarray(thr, dtype=np.float32), self.device)
+
+    def _scratch(self, key: str, nbytes: int) -> Optional[torch.Tensor]:
+        if nbytes == 0:
+            return None
+        t = self._work.get(key)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            self._work[key] = t
+        return t
+
+    # ------------------------------------------------------------------ PreComp tables
+    @staticmethod
+    def alias_indptr(indptr: np.ndarray) -> np.ndarray:
+        """[0, cumsum(deg^2)] as uint64 (reference pecanpy.py:469-476)."""
+        deg = (indptr[1:] - indptr[:-1]).astype(np.uint64)
+        out = np.zeros(indptr.size, dtype=np.uint64)
+        out[1:] = np.cumsum(deg * deg)
+        return out
+
+    def build_alias(self, indptr: np.ndarray, p: float, q: float, extend: bool = False, first_order: bool = False):
+        """Build the alias tables on the GPU and attach them to the handle."""
+        if self.kind != "csr":
+            raise ValueError("alias tables need a CSR graph")
+        gi = self.info()
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            wb = int(self.lib.b2w_alias_build_work_bytes(self.handle))
+            work = self._scratch("alias", wb)
+            if first_order:
+                tot = int(indptr[-1])
+                aj = torch.zeros(tot + gi.max_degree + 1, dtype=torch.int32, device=self.device)
+                aq = torch.zeros(tot + gi.max_degree + 1, dtype=torch.float32, device=self.device)
+                capi.check(self.lib.b2w_alias_build_first_order(self.handle, _ptr(aj), _ptr(aq), _ptr(work), wb,
+                                                                C.c_void_p(stream)), "b2w_alias_build_first_order")
+                aip_h, aip_d = None, None
+            else:
+                aip_h = self.alias_indptr(np.ascontiguousarray(indptr, dtype=np.uint32))
+                tot = int(aip_h[-1])
+                aip_d = _to_dev(aip_h, self.device, np.int64)
+                aj = torch.zeros(tot + gi.max_degree + 1, dtype=torch.int32, device=self.device)
+                aq = torch.zeros(tot + gi.max_degree + 1, dtype=torch.float32, device=self.device)
+                if extend and self.thr is None:
+                    raise ValueError("extend=True needs set_thresholds() first")
+                capi.check(self.lib.b2w_alias_build(self.handle, float(p), float(q), int(bool(extend)),
+                                                    _ptr(self.thr if extend else None), _ptr(aip_d), _ptr(aj), _ptr(aq),
+                                                    _ptr(work), wb, C.c_void_p(stream)), "b2w_alias_build")
+            capi.check(self.lib.b2w_graph_set_alias(self.handle, _ptr(aip_d), _ptr(aj), _ptr(aq)), "b2w_graph_set_alias")
+        self._keep["alias_indptr"], self._keep["alias_j"], self._keep["alias_q"] = aip_d, aj, aq
+        self.alias = (aip_h, aj[:tot], aq[:tot])
+        return self.alias
+
+    # ------------------------------------------------------------------ walking
+    def walk(self, mode, p: float, q: float, start, walk_length: int, seed: int = 0, *, extend: bool = False,
+             rng: int = capi.RNG_PHILOX, feed=None, row0: int = 0, flags: int = 0,
+             out: Optional[torch.Tensor] = None, collect_stats: bool = True) -> torch.Tensor:
+        """Walk ``len(start)`` rows on this GPU; returns an int32 *view* of the uint32 matrix
+        ``[n_rows, walk_length + 2]`` (layout of reference pecanpy.py:182-206) on the device."""
+        mode = MODES[mode] if isinstance(mode, str) else int(mode)
+        with torch.cuda.device(self.device):
+            if isinstance(start, torch.Tensor):
+                d_start = start.to(self.device)
+                if d_start.dtype not in (torch.int32, torch.uint32):
+                    d_start = d_start.to(torch.int32)
+                d_start = d_start.contiguous()
+            else:
+                d_start = _to_dev(np.ascontiguousarray(start, dtype=np.uint32), self.device, np.int32)
+            n_rows = d_start.numel()
+            ld = walk_length + 2
+            if out is None:
+                out = torch.empty((n_rows, ld), dtype=torch.int32, device=self.device)
+            elif out.shape[0] < n_rows or out.stride(0) < ld or out.stride(1) != 1 or out.element_size() != 4:
+                raise ValueError("out must be a row-major 4-byte integer tensor of at least [n_rows, L+2]")
+            d_feed = None
+            if rng == capi.RNG_FEED:
+                d_feed = feed if isinstance(feed, torch.Tensor) else _to_dev(np.ascontiguousarray(feed, np.float64), self.device)
+                if d_feed.numel() != n_rows * walk_length:
+                    raise ValueError("feed must hold n_rows * walk_length doubles")
+            wb = int(self.lib.b2w_walk_work_bytes(self.handle, mode))
+            work = self._scratch("walk", wb)
+            stats_t = torch.zeros(4, dtype=torch.int64, device=self.device) if collect_stats else None
+            thr = self.thr if extend else None
+            if extend and thr is None and mode in (capi.MODE_SPARSE_OTF, capi.MODE_DENSE_OTF):
+                raise ValueError("extend=True needs set_thresholds() first")
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            capi.check(self.lib.b2w_walk(self.handle, mode, float(p), float(q), int(bool(extend)), _ptr(thr),
+                                         _ptr(d_start), int(row0), n_rows, int(walk_length), int(seed) & (2 ** 64 - 1),
+                                         int(rng), _ptr(d_feed), _ptr(out), out.stride(0), _ptr(work), wb,
+                                         _ptr(stats_t), int(flags), C.c_void_p(stream)), "b2w_walk")
+            self.last_stats = stats_t
+        return out[:n_rows]
+
+    def stats(self) -> dict:
+        if self.last_stats is None:
+            return {}
+        s = self.last_stats.cpu().tolist()
+        return dict(steps=s[0], exact_replays=s[1], seq_sums=s[2], overflow_choices=s[3])
+
+    def walk_host(self, mode, p: float, q: float, start: np.ndarray, walk_length: int, seed: int = 0, *,
+                  extend: bool = False, row0: int = 0, flags: int = 0, batch_rows: int = 0,
+                  out: Optional[np.ndarray] = None) -> np.ndarray:
+        """End-to-end call with HOST buffers (b2w_walk_host): H2D of the start nodes, kernels and D2H of
+        the walk matrix are pipelined inside the library."""
+        mode = MODES[mode] if isinstance(mode, str) else int(mode)
+        start = np.ascontiguousarray(start, dtype=np.uint32)
+        n_rows = start.size
+        if out is None:
+            out = np.empty((n_rows, walk_length + 2), dtype=np.uint32)
+        assert out.dtype == np.uint32 and out.flags.c_contiguous and out.shape == (n_rows, walk_length + 2)
+        st = capi.WalkStats()
+        thr = self.thr if extend else None
+        with torch.cuda.device(self.device):
+            capi.check(self.lib.b2w_walk_host(self.handle, mode, float(p), float(q), int(bool(extend)), _ptr(thr),
+                                              C.c_void_p(start.ctypes.data), int(row0), n_rows, int(walk_length),
+                                              int(seed) & (2 ** 64 - 1), C.c_void_p(out.ctypes.data), int(batch_rows),
+                                              C.byref(st), int(flags)), "b2w_walk_host")
+        self.last_host_stats = dict(steps=st.steps, exact_replays=st.exact_replays, seq_sums=st.seq_sums,
+                                    overflow_choices=st.overflow_choices)
+        return out
+
+    def count_steps(self, walks: torch.Tensor, walk_length: int) -> int:
+        with torch.cuda.device(self.device):
+            acc = torch.zeros(1, dtype=torch.int64, device=self.device)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            capi.check(self.lib.b2w_count_steps(_ptr(walks), walks.shape[0], walk_length, walks.stride(0), _ptr(acc),
+                                                C.c_void_p(stream)), "b2w_count_steps")
+            return int(acc.item())
+
+
+def new_seed() -> int:
+    """Seed for random_state=None (reference: nondeterministic)."""
+    return int.from_bytes(os.urandom(8), "little")

@@ -1,0 +1,203 @@
+"""Graph containers: the input layout of the walk kernels.
+
+The reference's graph I/O (src/pecanpy/graph.py) is out of scope for the B200 engine and is not
+re-implemented feature for feature; these light containers exist so that the drop-in classes
+in :mod:`pecanpy_b200.pecanpy` can be constructed and loaded exactly like the reference's
+(``read_edg`` / ``read_npz`` / ``from_mat`` / ``save``; same attribute names and dtypes):
+
+* ``SparseGraph``: CSR ``indptr`` uint32[n+1], ``indices`` uint32[nnz] (rows sorted, unique),
+  ``data`` float32[nnz]   (reference graph.py:389-528, typing.py:31)
+* ``DenseGraph``:  ``data`` float64[n,n], ``nonzero`` bool[n,n] == (data != 0)  (graph.py:531-657)
+
+Node order follows the reference: first appearance in the edge list (graph.py:217-236).
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+
+class BaseGraph:
+    """Node-id bookkeeping (mirrors reference graph.py:19-105)."""
+
+    def __init__(self):
+        self._node_ids: List[str] = []
+        self._node_idmap: Dict[str, int] = {}
+
+    @property
+    def nodes(self) -> List[str]:
+        return self._node_ids
+
+    @property
+    def num_nodes(self) -> int:
+        return len(self._node_ids)
+
+    @property
+    def num_edges(self) -> int:
+        raise NotImplementedError
+
+    @property
+    def density(self) -> float:
+        return self.num_edges / self.num_nodes / (self.num_nodes - 1)
+
+    def set_node_ids(self, node_ids: Optional[Sequence[str]], implicit_ids: bool = False,
+                     num_nodes: Optional[int] = None):
+        if node_ids is not None and not implicit_ids:
+            self._node_ids = list(node_ids)
+        elif num_nodes is None:
+            raise ValueError("Need to specify `num_nodes` when setting implicit node IDs.")
+        else:
+            self._node_ids = [str(i) for i in range(num_nodes)]
+            if not implicit_ids:
+                warnings.warn("WARNING: Implicitly set node IDs to the canonical node ordering due to missing "
+                              "IDs field in the raw CSR npz file.", stacklevel=2)
+        self._node_idmap = {j: i for i, j in enumerate(self._node_ids)}
+
+
+def _read_edge_list(path: str, weighted: bool, directed: bool, delimiter: str = "\t"):
+    """Parse an ``.edg`` file into (ids, rows, cols, weights) with the reference's conventions:
+    first-seen node order, non-positive weights dropped with a warning, later duplicates win."""
+    ids: Dict[str, int] = {}
+    edges: Dict[tuple, float] = {}
+    with open(path, encoding="utf-8") as f:
+        for line in f:
+            terms = line.strip().split(delimiter)
+            a, b = terms[0].strip(), terms[1].strip()
+            w = 1.0
+            if weighted:
+                if len(terms) != 3:
+                    raise ValueError(f"Expecting three columns in the edge list file for a weighted graph, "
+                                     f"got {len(terms)} instead: {line!r}")
+                w = float(terms[-1])
+            if w <= 0:
+                warnings.warn(f"Non-positive edge ignored: w({a},{b}) = {w}", RuntimeWarning, stacklevel=2)
+                continue
+            ia = ids.setdefault(a, len(ids))
+            ib = ids.setdefault(b, len(ids))
+            edges[(ia, ib)] = w
+            if not directed:
+                edges[(ib, ia)] = w
+    names = [None] * len(ids)
+    for k, v in ids.items():
+        names[v] = k
+    if edges:
+        rc = np.array(list(edges.keys()), dtype=np.int64)
+        w = np.array(list(edges.values()), dtype=np.float64)
+        rows, cols = rc[:, 0], rc[:, 1]
+    else:
+        rows = cols = np.zeros(0, dtype=np.int64)
+        w = np.zeros(0, dtype=np.float64)
+    return names, rows, cols, w
+
+
+def _coo_to_csr(n: int, rows, cols, w):
+    order = np.lexsort((cols, rows))
+    rows, cols, w = rows[order], cols[order], w[order]
+    indptr = np.zeros(n + 1, dtype=np.uint32)
+    np.cumsum(np.bincount(rows, minlength=n), out=indptr[1:])
+    return indptr, cols.astype(np.uint32), w.astype(np.float32)
+
+
+class SparseGraph(BaseGraph):
+    def __init__(self):
+        super().__init__()
+        self.data: Optional[np.ndarray] = None
+        self.indptr: Optional[np.ndarray] = None
+        self.indices: Optional[np.ndarray] = None
+
+    @property
+    def num_edges(self) -> int:
+        if self.indptr is None:
+            raise ValueError("Empty graph.")
+        return int(self.indptr[-1])
+
+    def read_edg(self, path: str, weighted: bool, directed: bool, delimiter: str = "\t"):
+        names, rows, cols, w = _read_edge_list(path, weighted, directed, delimiter)
+        self.set_node_ids(names)
+        self.indptr, self.indices, self.data = _coo_to_csr(len(names), rows, cols, w)
+
+    def read_npz(self, path: str, weighted: bool, implicit_ids: bool = False):
+        raw = np.load(path)
+        self.indptr = raw["indptr"].astype(np.uint32)
+        self.indices = raw["indices"].astype(np.uint32)
+        self.data = raw["data"].astype(np.float32)
+        if not weighted:
+            self.data[:] = 1.0
+        ids = raw["IDs"] if "IDs" in raw.files else None
+        self.set_node_ids(ids, implicit_ids=implicit_ids, num_nodes=int(self.indptr.size - 1))
+
+    def save(self, path: str):
+        np.savez(path, IDs=self.nodes, data=self.data, indptr=self.indptr, indices=self.indices)
+
+    @classmethod
+    def from_mat(cls, adj_mat, node_ids: List[str], **kwargs):
+        g = cls(**kwargs)
+        g.set_node_ids(node_ids)
+        adj = np.asarray(adj_mat)
+        rows, cols = np.nonzero(adj)
+        g.indptr, g.indices, g.data = _coo_to_csr(adj.shape[0], rows, cols, adj[rows, cols].astype(np.float64))
+        return g
+
+    @classmethod
+    def from_csr(cls, indptr, indices, data, node_ids: Optional[List[str]] = None, **kwargs):
+        """Adopt ready CSR arrays (rows must be sorted and duplicate-free)."""
+        g = cls(**kwargs)
+        g.indptr = np.ascontiguousarray(indptr, dtype=np.uint32)
+        g.indices = np.ascontiguousarray(indices, dtype=np.uint32)
+        g.data = np.ascontiguousarray(data, dtype=np.float32)
+        g.set_node_ids(node_ids, implicit_ids=node_ids is None, num_nodes=int(g.indptr.size - 1))
+        return g
+
+
+class DenseGraph(BaseGraph):
+    def __init__(self):
+        super().__init__()
+        self._data: Optional[np.ndarray] = None
+        self._nonzero: Optional[np.ndarray] = None
+
+    @property
+    def num_edges(self) -> int:
+        if self._nonzero is None:
+            raise ValueError("Empty graph.")
+        return int(self._nonzero.sum())
+
+    @property
+    def data(self):
+        return self._data
+
+    @data.setter
+    def data(self, data):
+        self._data = np.ascontiguousarray(np.asarray(data).astype(float))
+        self._nonzero = np.array(self._data != 0, dtype=bool)
+
+    @property
+    def nonzero(self):
+        return self._nonzero
+
+    def read_npz(self, path: str, weighted: bool, implicit_ids: bool = False):
+        raw = np.load(path)
+        self.data = raw["data"]
+        if not weighted:
+            self.data = self.nonzero * 1.0
+        ids = raw["IDs"] if "IDs" in raw.files else None
+        self.set_node_ids(ids, implicit_ids=implicit_ids, num_nodes=self.data.shape[0])
+
+    def read_edg(self, path: str, weighted: bool, directed: bool, delimiter: str = "\t"):
+        names, rows, cols, w = _read_edge_list(path, weighted, directed, delimiter)
+        n = len(names)
+        mat = np.zeros((n, n))
+        mat[rows, cols] = w
+        self.set_node_ids(names)
+        self.data = mat
+
+    def save(self, path: str):
+        np.savez(path, data=self.data, IDs=self.nodes)
+
+    @classmethod
+    def from_mat(cls, adj_mat, node_ids: List[str], **kwargs):
+        g = cls(**kwargs)
+        g.data = adj_mat
+        g.set_node_ids(node_ids)
+        return g

@@ -1,0 +1,209 @@
+"""Drop-in walk generators with the API surface of ``pecanpy.pecanpy`` (reference
+src/pecanpy/pecanpy.py), backed by the B200 CUDA engine.
+
+Same class names, constructor signature ``(p, q, workers, verbose, extend, gamma, random_state)``
+(pecanpy.py:83-92), loaders (``read_edg`` / ``read_npz`` / ``from_mat``), and the methods
+``preprocess_transition_probs()``, ``simulate_walks(num_walks, walk_length) -> List[List[str]]``
+(pecanpy.py:116-162) and ``embed(...)`` (pecanpy.py:240-290).  ``simulate_walks_array`` returns
+the raw ``uint32[tot, L+2]`` matrix in the layout of ``Base._random_walks`` (pecanpy.py:182-206).
+
+What changes with respect to the reference:
+
+* the njit closure pair ``get_move_forward()`` / ``get_has_nbrs()`` cannot be called from a GPU;
+  the strategy is selected by the class (``_MODE``) instead;
+* random numbers: Philox4x32-10 keyed by ``(random_state, global walker row, step)`` instead of a
+  per-thread MT19937, so seeded walks are reproducible for ANY thread / GPU count (the reference
+  is reproducible only at one thread, pecanpy.py:51-55).  The start-node shuffle stays on the host
+  and is the reference's, verbatim (pecanpy.py:135-141);
+* there is no CPU fallback: without a CUDA device or the built extension the methods raise.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import numpy as np
+
+from .graph import BaseGraph, DenseGraph, SparseGraph
+
+
+class Base(BaseGraph):
+    _MODE = ""
+
+    def __init__(self, p: float = 1, q: float = 1, workers: int = 1, verbose: bool = False, extend: bool = False,
+                 gamma: float = 0, random_state: Optional[int] = None):
+        super().__init__()
+        self.p = p
+        self.q = q
+        self.workers = workers
+        self.verbose = verbose
+        self.extend = extend
+        self.gamma = gamma
+        self.random_state = random_state
+        self._preprocessed = False
+        self._engine = None
+        self.device = None          # torch device string/obj; None = current CUDA device
+        self.last_seed = None
+
+    # -- engine ------------------------------------------------------------------------------
+    def _make_engine(self):
+        raise NotImplementedError
+
+    @property
+    def engine(self):
+        if self._engine is None:
+            self._engine = self._make_engine()
+            if self.extend and self._MODE in ("SparseOTF", "DenseOTF", "PreComp"):
+                self._engine.set_thresholds(self.get_noise_thresholds())
+        return self._engine
+
+    def release(self):
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+            self._preprocessed = False
+
+    # -- reference surface ---------------------------------------------------------------------
+    def preprocess_transition_probs(self):
+        """Null default (pecanpy.py:231-233)."""
+
+    def _preprocess_transition_probs(self):
+        if not self._preprocessed:
+            self.preprocess_transition_probs()
+            self._preprocessed = True
+
+    def _start_nodes(self, num_walks: int) -> np.ndarray:
+        # pecanpy.py:135-141, verbatim semantics: NumPy legacy global generator
+        nodes = np.array(range(self.num_nodes), dtype=np.uint32)
+        start = np.concatenate([nodes] * num_walks)
+        np.random.seed(self.random_state)
+        np.random.shuffle(start)
+        return start
+
+    def _seed(self) -> int:
+        from .engine import new_seed
+        self.last_seed = new_seed() if self.random_state is None else int(self.random_state)
+        return self.last_seed
+
+    def simulate_walks_array(self, num_walks: int, walk_length: int) -> np.ndarray:
+        """Raw walk matrix ``uint32[num_nodes * num_walks, walk_length + 2]`` (host)."""
+        self._preprocess_transition_probs()
+        start = self._start_nodes(num_walks)
+        return self.engine.walk_host(self._MODE, self.p, self.q, start, walk_length, self._seed(),
+                                     extend=bool(self.extend))
+
+    def _map_walk(self, walk_idx_ary) -> List[str]:
+        end_idx = walk_idx_ary[-1]
+        return [self.nodes[i] for i in walk_idx_ary[:end_idx]]
+
+    def simulate_walks(self, num_walks: int, walk_length: int) -> List[List[str]]:
+        mat = self.simulate_walks_array(num_walks, walk_length)
+        ids = np.asarray(self.nodes, dtype=object)
+        lens = mat[:, -1]
+        return [ids[row[:n]].tolist() for row, n in zip(mat, lens)]
+
+    def embed(self, dim: int = 128, num_walks: int = 10, walk_length: int = 80, window_size: int = 10,
+              epochs: int = 1, verbose: bool = False):
+        try:
+            from gensim.models import Word2Vec
+        except ImportError as exc:  # pragma: no cover - gensim is not part of this image
+            raise ImportError("embed() needs gensim (the downstream Word2Vec consumer is out of scope "
+                              "for the B200 walk engine; simulate_walks works without it)") from exc
+        walks = self.simulate_walks(num_walks, walk_length)
+        w2v = Word2Vec(walks, vector_size=dim, window=window_size, sg=1, min_count=0, workers=self.workers,
+                       epochs=epochs, seed=self.random_state)
+        return w2v.wv[self.nodes]
+
+
+class _SparseBase(Base, SparseGraph):
+    def __init__(self, *args, **kwargs):
+        Base.__init__(self, *args, **kwargs)
+        self.data = None
+        self.indptr = None
+        self.indices = None
+
+    def _make_engine(self):
+        from .engine import WalkEngine
+        return WalkEngine.from_csr(self.indptr, self.indices, self.data, device=self.device)
+
+    def get_noise_thresholds(self) -> np.ndarray:
+        """mean + gamma * std of each row's weights, clipped at 0 (rw/sparse_rw.py:22-35; host NumPy,
+        as in the reference -- its pairwise f32 reductions are part of the bit-exact contract)."""
+        thr = np.zeros(self.num_nodes, dtype=np.float32)
+        data, indptr = self.data, self.indptr
+        with np.errstate(all="ignore"):
+            for i in range(self.num_nodes):
+                row = data[indptr[i]:indptr[i + 1]]
+                thr[i] = row.mean() + self.gamma * row.std()
+        return np.maximum(thr, 0)
+
+
+class SparseOTF(_SparseBase):
+    """Sparse graph, transition probabilities on the fly (reference pecanpy.py:510-561)."""
+    _MODE = "SparseOTF"
+
+
+class FirstOrderUnweighted(_SparseBase):
+    """Uniform first-order walks (reference pecanpy.py:293-309)."""
+    _MODE = "FirstOrderUnweighted"
+
+
+class PreComp(_SparseBase):
+    """Pre-computed 2nd-order alias tables (reference pecanpy.py:364-507); tables are built on the GPU."""
+    _MODE = "PreComp"
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.alias_dim = None
+        self.alias_j = None
+        self.alias_q = None
+        self.alias_indptr = None
+
+    def preprocess_transition_probs(self):
+        eng = self.engine
+        aip, aj, aq = eng.build_alias(self.indptr, self.p, self.q, extend=bool(self.extend))
+        self.alias_dim = (self.indptr[1:] - self.indptr[:-1]).astype(np.uint32)
+        self.alias_indptr = aip
+        self._alias_dev = (aj, aq)
+
+    def fetch_alias_tables(self):
+        """Copy the tables to the host as the reference's attributes (alias_j uint32, alias_q float32)."""
+        aj, aq = self._alias_dev
+        self.alias_j = aj.cpu().numpy().view(np.uint32)
+        self.alias_q = aq.cpu().numpy()
+        return self.alias_j, self.alias_q
+
+
+class PreCompFirstOrder(_SparseBase):
+    """Pre-computed first-order alias tables (reference pecanpy.py:312-361)."""
+    _MODE = "PreCompFirstOrder"
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.alias_j = self.alias_q = None
+
+    def preprocess_transition_probs(self):
+        _, aj, aq = self.engine.build_alias(self.indptr, 1.0, 1.0, first_order=True)
+        self._alias_dev = (aj, aq)
+
+
+class DenseOTF(Base, DenseGraph):
+    """Dense graph, transition probabilities on the fly (reference pecanpy.py:564-614)."""
+    _MODE = "DenseOTF"
+
+    def __init__(self, *args, **kwargs):
+        Base.__init__(self, *args, **kwargs)
+        self._data = None
+        self._nonzero = None
+
+    def _make_engine(self):
+        from .engine import WalkEngine
+        return WalkEngine.from_dense(self.data, self.nonzero, device=self.device)
+
+    def get_noise_thresholds(self) -> np.ndarray:
+        """rw/dense_rw.py:11-19 (host NumPy, as in the reference)."""
+        thr = np.zeros(self.num_nodes, dtype=np.float32)
+        with np.errstate(all="ignore"):
+            for i in range(self.num_nodes):
+                w = self.data[i, self.nonzero[i]]
+                thr[i] = w.mean() + self.gamma * w.std()
+        return np.maximum(thr, 0)
