@@ -66,6 +66,8 @@ typedef enum {
 #define B2W_FLAG_FORCE_EXACT_REPLAY 0x1u /* test hook: always take the sequential replay path */
 #define B2W_FLAG_NO_FILTER_STATS 0x2u    /* do not update the fallback counters */
 #define B2W_FLAG_THREAD_PER_WALKER 0x4u  /* SparseOTF: use the lane-per-walker kernel */
+#define B2W_FLAG_NO_UNWEIGHTED_KERNEL 0x8u /* SparseOTF: always use the generic (weight-streaming) kernel */
+#define B2W_FLAG_GROUP(n) (((uint32_t)(n) & 0xFFu) << 8) /* tuning: lanes per walker (8/16/32), 0 = auto */
 
 typedef struct b2w_graph b2w_graph; /* opaque */
 

@@ -17,6 +17,12 @@ RNG_PHILOX, RNG_FEED = 0, 1
 FLAG_FORCE_EXACT_REPLAY = 0x1
 FLAG_NO_FILTER_STATS = 0x2
 FLAG_THREAD_PER_WALKER = 0x4
+FLAG_NO_UNWEIGHTED_KERNEL = 0x8
+
+
+def FLAG_GROUP(n: int) -> int:
+    return (n & 0xFF) << 8
+
 GRAPH_CSR, GRAPH_DENSE, GRAPH_UNWEIGHTED, GRAPH_HAS_ALIAS = 0x1, 0x2, 0x4, 0x8
 
 EXPORTS = [

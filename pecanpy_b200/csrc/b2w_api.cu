@@ -191,7 +191,10 @@ void b2w_fill_bias_params(WalkParams& P, double p, double q) {
 
 extern "C" size_t b2w_walk_work_bytes(const b2w_graph* g, int mode) {
   if (!g) return 0;
-  if (mode == B2W_MODE_SPARSE_OTF && (g->flags & B2W_GRAPH_CSR)) return b2w_sparse_warp_work_bytes(g);
+  if (mode == B2W_MODE_SPARSE_OTF && (g->flags & B2W_GRAPH_CSR)) {
+    size_t a = b2w_sparse_warp_work_bytes(g), b = b2w_uw_work_bytes(g);
+    return a > b ? a : b;
+  }
   if (mode == B2W_MODE_DENSE_OTF) return 256;
   return 0;
 }
@@ -245,7 +248,11 @@ extern "C" int b2w_walk(const b2w_graph* g, int mode, double p, double q, int ex
   P.flags = flags; P.work = (float*)d_work; P.stats = d_stats;
   cudaStream_t s = (cudaStream_t)stream;
   if (dense) return b2w_launch_dense(g, ext, P, s);
-  if (warp_kernel) return b2w_launch_sparse_warp(g, P, s);
+  if (warp_kernel) {
+    // unweighted graphs with exactly representable biases: the membership-bitmap kernel
+    if (!ext && !(flags & B2W_FLAG_NO_UNWEIGHTED_KERNEL) && b2w_uw_eligible(g, p, q)) return b2w_launch_uw(g, P, s);
+    return b2w_launch_sparse_warp(g, P, s);
+  }
   return b2w_launch_thread_walk(g, mode, ext, P, s);
 }
 

@@ -151,4 +151,7 @@ int b2w_launch_sparse_warp(const b2w_graph* g, const WalkParams& P, cudaStream_t
 int b2w_launch_thread_walk(const b2w_graph* g, int mode, int extend, const WalkParams& P, cudaStream_t s);
 int b2w_launch_dense(const b2w_graph* g, int extend, const WalkParams& P, cudaStream_t s);
 size_t b2w_sparse_warp_work_bytes(const b2w_graph* g);
+bool b2w_uw_eligible(const b2w_graph* g, double p, double q);
+size_t b2w_uw_work_bytes(const b2w_graph* g);
+int b2w_launch_uw(const b2w_graph* g, const WalkParams& P, cudaStream_t s);
 uint32_t b2w_sparse_warp_total_warps(const b2w_graph* g);

@@ -1,0 +1,367 @@
+// b2w_walk_uw.cu -- SparseOTF node2vec on UNWEIGHTED graphs: the membership-bitmap kernel.
+//
+// PecanPy's default input is an unweighted edge list (`--weighted` off => data[:] = 1.0,
+// graph.py:479-480, cli.py), and BASELINE configs #1-#3 are unweighted.  Then every biased weight
+// of a step is one of three constants
+//     w_in = 1.0f,   w_out = f32(1/q),   w_ret = f32(1/p)            (rw/sparse_rw.py:86-87)
+// and the whole transition distribution of (cur, prev) is determined by
+//     deg(cur),  the POSITIONS in row(cur) of the common neighbours N(cur) & N(prev),  pos(prev).
+// So a step does not have to stream row(cur) at all:
+//   phase 1  membership -> bitmap over the positions of row(cur), searching whichever side is
+//            cheaper: every neighbour of cur in row(prev) (lane-parallel lower_bound, coalesced
+//            stream of row(cur)), or every neighbour of prev in row(cur) (touches only
+//            O(deg(prev) log deg(cur)) words of the hub row -- this is what makes power-law hubs
+//            cheap).  T groups of G lanes (G = 8/16/32) each own one walker, so a warp keeps
+//            32/G independent gather chains in flight.
+//   phase 2  normaliser S: the host verified that 1, w_out, w_ret are multiples of one power of two g
+//            and max_degree * max(w) < 2^24 g, so NO f32 partial sum can round and the reference's
+//            sequential f32 sum equals the exact count-weighted total.  probs take three values
+//            pa = fdiv(w_in,S), po = fdiv(w_out,S), pp = fdiv(w_ret,S)  (exact f32 quotients).
+//            The reference's cdf_k (sequential f32 cumsum, numba/np/arraymath.py:384-405) obeys
+//            |cdf_k - T_k| <= gamma_k T_k with T_k = n_in(k) pa + n_out(k) po + [pos(prev)<=k] pp
+//            (exact, f64 from counts).  Popcount prefix over the bitmap words locates the first
+//            word, then the first position k, with T_k (1 + e_k) >= u; if also T_k (1 - e_k) >= u the
+//            choice is proven (e_k = (k+2) 1.01 2^-24).  Otherwise the group replays the f32
+//            recurrence exactly from the bitmap (no memory traffic).
+// Bit-exact with the generic kernels and the oracle for every (cur, prev, u); dispatched only when
+// the exactness precondition holds (power-of-two-like p, q), else the generic stream kernel runs.
+//
+// Reference: pecanpy.py:164-210 (_random_walks), :522-561 (SparseOTF.get_move_forward),
+//            rw/sparse_rw.py:51-91 (get_normalized_probs), :142-230 (isnotin).
+#include <cmath>
+#include <cstring>
+
+#include "b2w_common.cuh"
+
+namespace {
+
+constexpr int UW_THREADS = 256;
+constexpr int UW_BW = 32;            // bitmap words of shared memory per group (rows up to 1024)
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+
+struct UwConsts {
+  float w_out, w_ret;                // f32(1/q), f32(1/p)
+  uint32_t gbm_stride;               // words of global bitmap scratch per group (0: never needed)
+  uint32_t* gbm;                     // global bitmap scratch
+};
+
+template <int G>
+struct Tile {
+  int lane, tl, base;
+  uint32_t mask;
+  __device__ __forceinline__ Tile() {
+    lane = threadIdx.x & 31;
+    tl = lane & (G - 1);
+    base = lane & ~(G - 1);
+    mask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << base);
+  }
+  __device__ __forceinline__ uint32_t ballot(bool p) const {
+    uint32_t b = __ballot_sync(mask, p);
+    return (G == 32) ? b : ((b >> base) & ((1u << G) - 1u));
+  }
+  template <typename T>
+  __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(mask, v, src, G); }
+  __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+  __device__ __forceinline__ uint32_t incl_scan(uint32_t v) const {
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) {
+      uint32_t t = __shfl_up_sync(mask, v, o, G);
+      if (tl >= o) v += t;
+    }
+    return v;
+  }
+  __device__ __forceinline__ uint32_t sum(uint32_t v) const {
+#pragma unroll
+    for (int o = G / 2; o; o >>= 1) v += __shfl_xor_sync(mask, v, o, G);
+    return v;
+  }
+  __device__ __forceinline__ uint32_t minu(uint32_t v) const {
+#pragma unroll
+    for (int o = G / 2; o; o >>= 1) v = min(v, __shfl_xor_sync(mask, v, o, G));
+    return v;
+  }
+};
+
+template <int G>
+__global__ void __launch_bounds__(UW_THREADS) walk_uw_kernel(const WalkParams P, const UwConsts C) {
+  constexpr int GROUPS = UW_THREADS / G;
+  __shared__ uint32_t s_bm[GROUPS][UW_BW];
+  const Tile<G> T;
+  const int gib = threadIdx.x / G;                                   // group in block
+  const uint32_t ggid = blockIdx.x * GROUPS + gib;                    // global group id
+  uint32_t* const gbm = C.gbm + (size_t)ggid * C.gbm_stride;
+  const uint32_t L = P.L;
+  const double EC = 1.01 * 5.9604644775390625e-08;                    // 1.01 * 2^-24
+  uint32_t st_steps = 0, st_replays = 0, st_overflow = 0;
+
+  for (;;) {
+    unsigned long long i = 0;
+    if (T.tl == 0) i = atomicAdd(P.counter, 1ull);
+    i = T.shfl(i, 0);
+    if (i >= P.n_rows) break;
+    uint32_t* const out = P.out + i * P.ld_out;
+    uint32_t cur = __ldg(P.start + i);
+    uint32_t prev = 0, ps = 0, pdeg = 0;
+    uint32_t cs = __ldg(P.indptr + cur);
+    uint32_t ce = __ldg(P.indptr + cur + 1);
+    uint32_t eff = L + 1;
+    uint32_t myval = (T.tl == 0) ? cur : 0u;                          // lane (e mod G) holds output entry e
+    double my_u = 0.0;
+    uint32_t j = 1;
+    for (; j <= L; ++j) {
+      const uint32_t d = ce - cs;
+      if (d == 0) { eff = j; break; }                                 // pecanpy.py:194-196, 204-206
+      if (((j - 1) & (G - 1)) == 0) {
+        const uint32_t sj = j + T.tl;
+        if (sj <= L) my_u = step_uniform(P, i, sj);
+      }
+      const double u = T.shfl(my_u, (j - 1) & (G - 1));
+      const bool has_prev = j > 1;
+      const uint32_t nwords = (d + 31) >> 5;
+      uint32_t* const bm = (nwords <= UW_BW) ? s_bm[gib] : gbm;
+
+      // ---------------- phase 1: membership bitmap over the positions of row(cur)
+      uint32_t m = 0, kp = NONE;
+      if (has_prev) {
+        for (uint32_t w = T.tl; w < nwords; w += G) bm[w] = 0u;
+        T.sync();
+        const uint32_t lgp = 32 - __clz(pdeg), lgd = 32 - __clz(d);
+        const uint32_t fwd_cost = ((d + G - 1) / G) * lgp;
+        const uint32_t rev_cost = ((pdeg + 1 + G - 1) / G) * lgd;
+        if (fwd_cost <= rev_cost) {
+          // every neighbour of cur looked up in row(prev)
+          for (uint32_t c0 = 0; c0 < d; c0 += G) {
+            const uint32_t k = c0 + T.tl;
+            const bool valid = k < d;
+            const uint32_t x = valid ? __ldg(P.indices + cs + k) : NONE;
+            uint32_t lo = 0, hi = pdeg;
+            bool found = false;
+            for (uint32_t it = 0; it < lgp; ++it) {
+              if (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                const uint32_t v = __ldg(P.indices + ps + mid);
+                found |= (v == x);
+                if (v < x) lo = mid + 1; else hi = mid;
+              }
+            }
+            const bool isprev = valid && (x == prev);
+            const uint32_t bprev = T.ballot(isprev);
+            if (bprev) kp = c0 + __ffs(bprev) - 1;
+            const uint32_t bal = T.ballot(valid && found && !isprev);
+            if (bal) {
+              if (T.tl == 0) {
+                if (G == 32) bm[c0 >> 5] = bal; else bm[c0 >> 5] |= bal << (c0 & 31);
+              }
+              m += __popc(bal);
+            }
+          }
+        } else {
+          // every neighbour of prev (and prev itself, last key) looked up in row(cur)
+          const uint32_t nkeys = pdeg + 1;
+          uint32_t mloc = 0, kploc = NONE;
+          for (uint32_t c0 = 0; c0 < nkeys; c0 += G) {
+            const uint32_t ii = c0 + T.tl;
+            const bool valid = ii < nkeys;
+            const uint32_t y = valid ? (ii < pdeg ? __ldg(P.indices + ps + ii) : prev) : NONE;
+            uint32_t lo = 0, hi = d, pos = NONE;
+            for (uint32_t it = 0; it < lgd; ++it) {
+              if (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                const uint32_t v = __ldg(P.indices + cs + mid);
+                if (v == y) pos = mid;
+                if (v < y) lo = mid + 1; else hi = mid;
+              }
+            }
+            if (valid && pos != NONE) {
+              if (ii == pdeg) kploc = pos;
+              else if (y != prev) { atomicOr(&bm[pos >> 5], 1u << (pos & 31)); ++mloc; }
+            }
+          }
+          m = T.sum(mloc);
+          kp = T.minu(kploc);
+        }
+        T.sync();
+      }
+
+      // ---------------- phase 2: exact normaliser, three-valued probabilities
+      const float w_o = has_prev ? C.w_out : 1.0f;                    // first step: every weight is 1
+      const uint32_t h = (kp != NONE) ? 1u : 0u;
+      const uint32_t n_o = d - m - h;
+      const double Tw = (double)m + (double)n_o * (double)w_o + (double)h * (double)C.w_ret;
+      const float S = (float)Tw;                                      // exact (host-verified precondition)
+      const double pa = (double)__fdiv_rn(1.0f, S);
+      const double po = (double)__fdiv_rn(w_o, S);
+      const double pp = (double)__fdiv_rn(C.w_ret, S);
+
+      uint32_t choice = d;                                            // default: cdf[-1] < u (overflow)
+      bool replay = (P.flags & B2W_FLAG_FORCE_EXACT_REPLAY) != 0;
+      if (!replay) {
+        // word level: first word whose last position possibly reaches u
+        uint32_t carry = 0, wsel = NONE, bits_sel = 0, nc_before = 0;
+        for (uint32_t w0 = 0; w0 < nwords; w0 += G) {
+          const uint32_t w = w0 + T.tl;
+          const bool valid = w < nwords;
+          const uint32_t bits = (valid && has_prev) ? bm[w] : 0u;
+          const uint32_t cnt = __popc(bits);
+          const uint32_t incl = T.incl_scan(cnt) + carry;
+          const uint32_t kend = min(d, (w + 1) << 5) - 1;
+          const uint32_t hk = (kp <= kend) ? 1u : 0u;                 // NONE compares false
+          const double Tk = (double)incl * pa + (double)(kend + 1 - incl - hk) * po + (double)hk * pp;
+          const double hi_b = Tk + Tk * (EC * (double)(kend + 2));
+          const uint32_t bal = T.ballot(valid && (hi_b >= u));
+          if (bal) {
+            const int src = __ffs(bal) - 1;
+            wsel = w0 + src;
+            bits_sel = T.shfl(bits, src);
+            nc_before = T.shfl(incl - cnt, src);
+            break;
+          }
+          carry = T.shfl(incl, G - 1);
+        }
+        if (wsel != NONE) {
+          // position level inside the selected word
+          bool decided = false;
+#pragma unroll
+          for (int r = 0; r < 32 / G; ++r) {
+            const uint32_t b = r * G + T.tl;
+            const uint32_t k = (wsel << 5) + b;
+            const bool valid = k < d;
+            const uint32_t nc = nc_before + __popc(bits_sel & (0xFFFFFFFFu >> (31 - b)));
+            const uint32_t hk = (kp <= k) ? 1u : 0u;
+            const double Tk = (double)nc * pa + (double)(k + 1 - nc - hk) * po + (double)hk * pp;
+            const double Ek = Tk * (EC * (double)(k + 2));
+            const uint32_t bp = T.ballot(valid && (Tk + Ek >= u));
+            if (!decided && bp) {
+              const int fp = __ffs(bp) - 1;
+              const bool sure = T.shfl((Tk - Ek >= u) ? 1 : 0, fp) != 0;
+              if (sure) choice = (wsel << 5) + r * G + fp; else replay = true;
+              decided = true;
+            }
+          }
+          if (!decided) replay = true;                               // rounding at the word boundary
+        }
+      }
+      if (replay) {
+        // ---------------- exact replay of the sequential f32 cumsum from the bitmap
+        const float fa = (float)pa, fo = (float)po, fp_ = (float)pp;
+        float cdf = 0.f;
+        choice = d;
+        uint32_t k = 0;
+        for (uint32_t w = 0; w < nwords && choice == d; ++w) {
+          const uint32_t bits = has_prev ? bm[w] : 0u;
+          const uint32_t nb = min(32u, d - (w << 5));
+          for (uint32_t b = 0; b < nb; ++b, ++k) {
+            float v = ((bits >> b) & 1u) ? fa : fo;
+            if (k == kp) v = fp_;
+            cdf = __fadd_rn(cdf, v);
+            if (!((double)cdf < u)) { choice = k; break; }
+          }
+        }
+        ++st_replays;
+      }
+      if (choice == d) ++st_overflow;
+      T.sync();                                                       // bitmap is rewritten by the next step
+
+      const uint32_t nxt = __ldg(P.indices + cs + choice);            // unchecked, as pecanpy.py:559
+      if (T.tl == (j & (G - 1))) myval = nxt;
+      if ((j & (G - 1)) == G - 1) {
+        out[(j & ~(uint32_t)(G - 1)) + T.tl] = myval;
+        myval = 0u;
+      }
+      prev = cur; ps = cs; pdeg = d;
+      cur = nxt;
+      cs = __ldg(P.indptr + cur);
+      ce = __ldg(P.indptr + cur + 1);
+      ++st_steps;
+    }
+    // tail: the G-block holding entry j (first entry not produced), then zeros, then eff at L+1
+    const uint32_t blk = j & ~(uint32_t)(G - 1);
+    for (uint32_t b0 = blk; b0 < L + 2; b0 += G) {
+      const uint32_t e = b0 + T.tl;
+      uint32_t v = (b0 == blk) ? myval : 0u;
+      if (e == L + 1) v = eff;
+      if (e < L + 2) out[e] = v;
+    }
+  }
+  if (P.stats && !(P.flags & B2W_FLAG_NO_FILTER_STATS) && T.tl == 0) {
+    if (st_steps) atomicAdd((unsigned long long*)&P.stats->steps, (unsigned long long)st_steps);
+    if (st_replays) atomicAdd((unsigned long long*)&P.stats->exact_replays, (unsigned long long)st_replays);
+    if (st_overflow) atomicAdd((unsigned long long*)&P.stats->overflow_choices, (unsigned long long)st_overflow);
+  }
+}
+
+template <int G>
+int grid_blocks(const b2w_graph* g) {
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, walk_uw_kernel<G>, UW_THREADS, 0);
+  if (per_sm < 1) per_sm = 1;
+  return per_sm * g->num_sms;
+}
+
+int pick_group(const b2w_graph* g, uint32_t flags) {
+  uint32_t forced = (flags >> 8) & 0xFF;                             // debug/tuning: bits 8..15 = group size
+  if (forced == 8 || forced == 16 || forced == 32) return (int)forced;
+  double avg = g->n ? (double)g->nnz / g->n : 0.0;
+  return avg <= 12.0 ? 8 : (avg <= 48.0 ? 16 : 32);
+}
+
+uint32_t max_groups(const b2w_graph* g) {
+  int b8 = grid_blocks<8>(g), b16 = grid_blocks<16>(g), b32 = grid_blocks<32>(g);
+  uint32_t a = (uint32_t)b8 * (UW_THREADS / 8), b = (uint32_t)b16 * (UW_THREADS / 16), c = (uint32_t)b32 * (UW_THREADS / 32);
+  return max(a, max(b, c));
+}
+
+uint32_t gbm_stride(const b2w_graph* g) {
+  uint32_t words = (g->max_degree + 31) / 32;
+  return words > (uint32_t)UW_BW ? ((words + 3) & ~3u) : 0u;
+}
+
+}  // namespace
+
+// Exactness precondition of the analytic normaliser: 1, f32(1/q), f32(1/p) are multiples of one
+// power of two g and (max_degree + 1) * max(w) < 2^24 g.
+bool b2w_uw_eligible(const b2w_graph* g, double p, double q) {
+  if (!(g->flags & B2W_GRAPH_UNWEIGHTED)) return false;
+  const float w[3] = {1.0f, (float)(1.0 / q), (float)(1.0 / p)};
+  int low = 1000;
+  float mx = 0.f;
+  for (float v : w) {
+    if (!(v > 0.f) || !(v < 3.0e38f)) return false;
+    uint32_t bits;
+    memcpy(&bits, &v, 4);
+    uint32_t expo = (bits >> 23) & 0xFF, man = bits & 0x7FFFFF;
+    if (expo == 0) return false;                                      // denormal
+    man |= 0x800000;
+    int tz = __builtin_ctz(man);
+    int e = (int)expo - 127 - 23 + tz;                                // exponent of the lowest set bit
+    if (e < low) low = e;
+    if (v > mx) mx = v;
+  }
+  double lim = ldexp(1.0, 24 + low);
+  return ((double)g->max_degree + 1.0) * (double)mx < lim;
+}
+
+size_t b2w_uw_work_bytes(const b2w_graph* g) {
+  return 256 + (size_t)max_groups(g) * gbm_stride(g) * sizeof(uint32_t);
+}
+
+int b2w_launch_uw(const b2w_graph* g, const WalkParams& P_in, cudaStream_t s) {
+  WalkParams P = P_in;
+  char* base = reinterpret_cast<char*>(P_in.work);
+  P.counter = reinterpret_cast<unsigned long long*>(base);
+  UwConsts C;
+  C.w_out = (float)(1.0 / P.q);
+  C.w_ret = (float)(1.0 / P.p);
+  C.gbm = reinterpret_cast<uint32_t*>(base + 256);
+  C.gbm_stride = gbm_stride(g);
+  B2W_CUDA(cudaMemsetAsync(P.counter, 0, 8, s));
+  const int G = pick_group(g, P.flags);
+  int blocks = G == 8 ? grid_blocks<8>(g) : (G == 16 ? grid_blocks<16>(g) : grid_blocks<32>(g));
+  uint64_t groups_per_block = UW_THREADS / G;
+  uint64_t need = (P.n_rows + groups_per_block - 1) / groups_per_block;
+  if ((uint64_t)blocks > need) blocks = (int)(need ? need : 1);
+  if (G == 8) walk_uw_kernel<8><<<blocks, UW_THREADS, 0, s>>>(P, C);
+  else if (G == 16) walk_uw_kernel<16><<<blocks, UW_THREADS, 0, s>>>(P, C);
+  else walk_uw_kernel<32><<<blocks, UW_THREADS, 0, s>>>(P, C);
+  return b2w_cuda_fail(cudaGetLastError(), "walk_uw_kernel launch");
+}

@@ -63,12 +63,18 @@ def test_philox_device_known_answers(mods):
         assert list(o) == want
 
 
+# b2w_walk flags: 1 forced replay, 4 lane-per-walker kernel, 8 generic (weight-streaming) kernel even on
+# unweighted graphs, bits 8..15 lanes per walker of the unweighted membership-bitmap kernel
+FLAG_SETS = {"auto": 0, "auto-replay": 1, "lane-per-walker": 4, "generic": 8, "generic-replay": 9,
+             "uw-g8": 8 << 8, "uw-g16": 16 << 8, "uw-g32": 32 << 8, "uw-g8-replay": (8 << 8) | 1,
+             "uw-g32-replay": (32 << 8) | 1}
+
 SPARSE_R1 = ["testwalk_SparseOTF", "karate_sparseotf_p1_q1", "karate_sparseotf_p05_q2", "karate_sparseotf_p03_q07",
              "w200_sparseotf_n2v", "w200_sparseotf_ext_g0", "w200_sparseotf_ext_g05", "hub400_sparseotf_n2v",
              "hub400_sparseotf_ext", "uhub400_sparseotf_n2v"]
 
 
-@pytest.mark.parametrize("flags", [0, 1, 4], ids=["filter", "forced-replay", "lane-per-walker"])
+@pytest.mark.parametrize("flags", list(FLAG_SETS.values()), ids=list(FLAG_SETS))
 @pytest.mark.parametrize("name", SPARSE_R1)
 def test_sparse_otf_replays_reference_R1(mods, name, flags):
     """MT-replay: feed the reference's uniforms; rows that never dead-end consume exactly L doubles in
@@ -108,7 +114,7 @@ ALL_SPARSE = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOL
                     if "sparseotf" in f or "SparseOTF" in f)
 
 
-@pytest.mark.parametrize("flags", [0, 1, 4], ids=["filter", "forced-replay", "lane-per-walker"])
+@pytest.mark.parametrize("flags", list(FLAG_SETS.values()), ids=list(FLAG_SETS))
 @pytest.mark.parametrize("name", ALL_SPARSE)
 def test_sparse_otf_philox_R2(mods, name, flags):
     c = load(name)
@@ -195,6 +201,37 @@ def test_dense_otf_philox_R2(mods, name, flags):
     got = to_np(eng.walk("DenseOTF", float(c["p"]), float(c["q"]), c["start"], L, seed=77, extend=ext, flags=flags))
     assert np.array_equal(got, want), first_diff(got, want)
     eng.close()
+
+
+@pytest.mark.parametrize("flags", list(FLAG_SETS.values()), ids=list(FLAG_SETS))
+@pytest.mark.parametrize("pq", [(4.0, 0.25), (0.5, 2.0), (1.0, 1.0), (0.3, 0.7)])
+def test_power_law_hubs_unweighted(mods, pq, flags):
+    """Unweighted power-law graph with hub rows above 1024 neighbours (global bitmap / scratch rows, both
+    search directions, multi-word prefix); every kernel variant must equal the oracle."""
+    from pecanpy_b200.synth import power_law_csr
+    orc = mods["orc"]
+    indptr, indices, data = power_law_csr(20000, 800000, seed=5)
+    assert int((indptr[1:] - indptr[:-1]).max()) > 1100
+    start = orc.shuffled_start(20000, 1, 3)[:6000]
+    p, q = pq
+    want = orc.walk_csr("SparseOTF", indptr, indices, data, p, q, start, 24, rng=orc.RNG_PHILOX, seed=21)
+    eng = mods["WalkEngine"].from_csr(indptr, indices, data)
+    got = to_np(eng.walk("SparseOTF", p, q, start, 24, seed=21, flags=flags))
+    assert np.array_equal(got, want), first_diff(got, want)
+    eng.close()
+
+
+def test_power_law_hubs_weighted(mods):
+    from pecanpy_b200.synth import power_law_csr
+    orc = mods["orc"]
+    indptr, indices, data = power_law_csr(20000, 800000, seed=6, weighted=True)
+    start = orc.shuffled_start(20000, 1, 4)[:4000]
+    for flags in (0, 1, 4):
+        want = orc.walk_csr("SparseOTF", indptr, indices, data, 0.5, 2.0, start, 16, rng=orc.RNG_PHILOX, seed=22)
+        eng = mods["WalkEngine"].from_csr(indptr, indices, data)
+        got = to_np(eng.walk("SparseOTF", 0.5, 2.0, start, 16, seed=22, flags=flags))
+        assert np.array_equal(got, want), first_diff(got, want)
+        eng.close()
 
 
 def test_row_sharding_invariance_and_host_wrapper(mods):
