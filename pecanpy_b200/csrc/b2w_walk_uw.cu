@@ -41,6 +41,7 @@ constexpr uint32_t NONE = 0xFFFFFFFFu;
 
 struct UwConsts {
   float w_out, w_ret;                // f32(1/q), f32(1/p)
+  int out_pow2, ret_pow2;            // w_out / w_ret are powers of two in [2^-20, 2^20]: fdiv(w,S) == fa * w
   uint32_t gbm_stride;               // words of global bitmap scratch per group (0: never needed)
   uint32_t* gbm;                     // global bitmap scratch
 };
@@ -82,6 +83,97 @@ struct Tile {
   }
 };
 
+// Number of elements of the sorted row[0..n) that are < x.  Branch-free, `lg` = 32 - clz(n)
+// iterations (uniform across the group): pos only grows over a prefix of elements < x.
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__ row, uint32_t n, uint32_t x,
+                                                    uint32_t lg) {
+  uint32_t pos = 0;
+  for (uint32_t step = lg ? (1u << (lg - 1)) : 0u; step; step >>= 1) {
+    const uint32_t idx = pos + step;
+    const uint32_t v = __ldg(row + (min(idx, n) - 1));
+    if (idx <= n && v < x) pos = idx;
+  }
+  return pos;
+}
+
+__device__ __forceinline__ double pow2_double(int e) { return __hiloint2double((1023 + e) << 20, 0); }
+
+// Adds `fo` to the running f32 prefix `cdf` n times, exactly as n sequential __fadd_rn would, but
+// jumping through each binade of cdf in O(1): while cdf stays inside one binade its grid is
+// g = ulp(cdf), cdf is a multiple of g, and RN(cdf + fo) = cdf + RN_g(fo) whenever fo/g is not a
+// rounding tie (ties and binade crossings fall back to genuine single additions).  `k` is the
+// index of the next element; returns true and sets `choice` at the first element with !(cdf < u).
+__device__ __forceinline__ bool advance_run(float& cdf, uint32_t& k, uint32_t n, const float fo, const double u,
+                                            uint32_t& choice) {
+  while (n > 0) {
+    const uint32_t bits = __float_as_uint(cdf);
+    const int ex = (int)((bits >> 23) & 0xFFu);
+    if (ex >= 1 && ex < 255) {
+      const double t = (double)fo * pow2_double(150 - ex);            // fo / g, exact
+      if (t < 8388608.0) {
+        const double tr = rint(t);
+        if (fabs(t - tr) != 0.5) {
+          const uint32_t R = (uint32_t)tr;
+          if (R == 0) { k += n; return false; }                       // fo is absorbed: cdf never moves again
+          const uint32_t Cm = (bits & 0x7FFFFFu) | 0x800000u;         // cdf / g in [2^23, 2^24)
+          const uint32_t imax = (0xFFFFFFu - Cm) / R;                 // additions that stay below 2^24 g
+          const uint32_t steps = min(n, imax);
+          if (steps > 0) {
+            const uint32_t Cn = Cm + steps * R;
+            const float cdf_n = __uint_as_float((bits & 0xFF800000u) | (Cn & 0x7FFFFFu));
+            if (!((double)cdf_n < u)) {
+              const double U = u * pow2_double(150 - ex);             // u / g, exact scaling
+              double di = ceil((U - (double)Cm) / (double)R);
+              uint32_t i = di < 1.0 ? 1u : (di > (double)steps ? steps : (uint32_t)di);
+              while (i > 1 && (double)(Cm + (i - 1) * R) >= U) --i;
+              while ((double)(Cm + i * R) < U) ++i;
+              choice = k + i - 1;
+              return true;
+            }
+            cdf = cdf_n; k += steps; n -= steps;
+            if (n == 0) return false;
+          }
+        }
+      }
+    }
+    cdf = __fadd_rn(cdf, fo);                                          // genuine addition
+    if (!((double)cdf < u)) { choice = k; return true; }
+    ++k; --n;
+  }
+  return false;
+}
+
+template <int G>
+__device__ __noinline__ uint32_t replay_exact(const uint32_t* __restrict__ bm, const bool has_bm,
+                                              const uint32_t nwords, const uint32_t d, const uint32_t kp, const float fa,
+                                              const float fo, const float fp, const double u) {
+  const Tile<G> T;
+  float cdf = 0.f;
+  uint32_t k = 0, choice = d;
+  for (uint32_t w0 = 0; w0 < nwords; w0 += G) {
+    const uint32_t w = w0 + T.tl;
+    uint32_t bits = (has_bm && w < nwords) ? bm[w] : 0u;
+    if (kp != NONE && (kp >> 5) == w) bits |= 1u << (kp & 31);
+    uint32_t nz = T.ballot(bits != 0u);
+    while (nz) {
+      const int src = __ffs(nz) - 1;
+      nz &= nz - 1;
+      uint32_t wb = T.shfl(bits, src);
+      const uint32_t wbase = (w0 + src) << 5;
+      while (wb) {
+        const uint32_t pos = wbase + __ffs(wb) - 1;
+        wb &= wb - 1;
+        if (advance_run(cdf, k, pos - k, fo, u, choice)) return choice;
+        cdf = __fadd_rn(cdf, pos == kp ? fp : fa);                    // the special element at `pos`
+        if (!((double)cdf < u)) return pos;
+        k = pos + 1;
+      }
+    }
+  }
+  if (advance_run(cdf, k, d - k, fo, u, choice)) return choice;
+  return d;                                                           // cdf[-1] < u: the reference's overflow
+}
+
 template <int G>
 __global__ void __launch_bounds__(UW_THREADS) walk_uw_kernel(const WalkParams P, const UwConsts C) {
   constexpr int GROUPS = UW_THREADS / G;
@@ -101,7 +193,8 @@ __global__ void __launch_bounds__(UW_THREADS) walk_uw_kernel(const WalkParams P,
     if (i >= P.n_rows) break;
     uint32_t* const out = P.out + i * P.ld_out;
     uint32_t cur = __ldg(P.start + i);
-    uint32_t prev = 0, ps = 0, pdeg = 0;
+    uint32_t prev = 0, pdeg = 0;
+    const uint32_t* prow = P.indices;
     uint32_t cs = __ldg(P.indptr + cur);
     uint32_t ce = __ldg(P.indptr + cur + 1);
     uint32_t eff = L + 1;
@@ -119,60 +212,43 @@ __global__ void __launch_bounds__(UW_THREADS) walk_uw_kernel(const WalkParams P,
       const bool has_prev = j > 1;
       const uint32_t nwords = (d + 31) >> 5;
       uint32_t* const bm = (nwords <= UW_BW) ? s_bm[gib] : gbm;
+      const uint32_t* const crow = P.indices + cs;
 
       // ---------------- phase 1: membership bitmap over the positions of row(cur)
       uint32_t m = 0, kp = NONE;
       if (has_prev) {
-        for (uint32_t w = T.tl; w < nwords; w += G) bm[w] = 0u;
-        T.sync();
         const uint32_t lgp = 32 - __clz(pdeg), lgd = 32 - __clz(d);
-        const uint32_t fwd_cost = ((d + G - 1) / G) * lgp;
-        const uint32_t rev_cost = ((pdeg + 1 + G - 1) / G) * lgd;
+        const uint32_t fwd_cost = ((d + G - 1) / G) * (lgp + 2);
+        const uint32_t rev_cost = ((pdeg + G) / G) * (lgd + 2) + (nwords + G - 1) / G;
         if (fwd_cost <= rev_cost) {
-          // every neighbour of cur looked up in row(prev)
+          // every neighbour of cur looked up in row(prev); each bitmap word is written, none needs clearing
           for (uint32_t c0 = 0; c0 < d; c0 += G) {
             const uint32_t k = c0 + T.tl;
             const bool valid = k < d;
-            const uint32_t x = valid ? __ldg(P.indices + cs + k) : NONE;
-            uint32_t lo = 0, hi = pdeg;
-            bool found = false;
-            for (uint32_t it = 0; it < lgp; ++it) {
-              if (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                const uint32_t v = __ldg(P.indices + ps + mid);
-                found |= (v == x);
-                if (v < x) lo = mid + 1; else hi = mid;
-              }
-            }
+            const uint32_t x = valid ? __ldg(crow + k) : NONE;
+            const uint32_t pos = lower_bound_u32(prow, pdeg, x, lgp);
+            const bool found = pos < pdeg && __ldg(prow + pos) == x;
             const bool isprev = valid && (x == prev);
             const uint32_t bprev = T.ballot(isprev);
             if (bprev) kp = c0 + __ffs(bprev) - 1;
             const uint32_t bal = T.ballot(valid && found && !isprev);
-            if (bal) {
-              if (T.tl == 0) {
-                if (G == 32) bm[c0 >> 5] = bal; else bm[c0 >> 5] |= bal << (c0 & 31);
-              }
-              m += __popc(bal);
+            if (T.tl == 0) {
+              if (G == 32 || (c0 & 31) == 0) bm[c0 >> 5] = bal; else bm[c0 >> 5] |= bal << (c0 & 31);
             }
+            m += __popc(bal);
           }
         } else {
           // every neighbour of prev (and prev itself, last key) looked up in row(cur)
+          for (uint32_t w = T.tl; w < nwords; w += G) bm[w] = 0u;
+          T.sync();
           const uint32_t nkeys = pdeg + 1;
           uint32_t mloc = 0, kploc = NONE;
           for (uint32_t c0 = 0; c0 < nkeys; c0 += G) {
             const uint32_t ii = c0 + T.tl;
             const bool valid = ii < nkeys;
-            const uint32_t y = valid ? (ii < pdeg ? __ldg(P.indices + ps + ii) : prev) : NONE;
-            uint32_t lo = 0, hi = d, pos = NONE;
-            for (uint32_t it = 0; it < lgd; ++it) {
-              if (lo < hi) {
-                const uint32_t mid = (lo + hi) >> 1;
-                const uint32_t v = __ldg(P.indices + cs + mid);
-                if (v == y) pos = mid;
-                if (v < y) lo = mid + 1; else hi = mid;
-              }
-            }
-            if (valid && pos != NONE) {
+            const uint32_t y = valid ? (ii < pdeg ? __ldg(prow + ii) : prev) : NONE;
+            const uint32_t pos = lower_bound_u32(crow, d, y, lgd);
+            if (valid && pos < d && __ldg(crow + pos) == y) {
               if (ii == pdeg) kploc = pos;
               else if (y != prev) { atomicOr(&bm[pos >> 5], 1u << (pos & 31)); ++mloc; }
             }
@@ -187,54 +263,62 @@ __global__ void __launch_bounds__(UW_THREADS) walk_uw_kernel(const WalkParams P,
       const float w_o = has_prev ? C.w_out : 1.0f;                    // first step: every weight is 1
       const uint32_t h = (kp != NONE) ? 1u : 0u;
       const uint32_t n_o = d - m - h;
-      const double Tw = (double)m + (double)n_o * (double)w_o + (double)h * (double)C.w_ret;
+      const double Tw = fma((double)n_o, (double)w_o, fma((double)h, (double)C.w_ret, (double)m));   // exact
       const float S = (float)Tw;                                      // exact (host-verified precondition)
-      const double pa = (double)__fdiv_rn(1.0f, S);
-      const double po = (double)__fdiv_rn(w_o, S);
-      const double pp = (double)__fdiv_rn(C.w_ret, S);
+      const float fa = __fdiv_rn(1.0f, S);
+      const float fo = !has_prev ? fa : (C.out_pow2 ? __fmul_rn(fa, w_o) : __fdiv_rn(w_o, S));
+      const float fp = C.ret_pow2 ? __fmul_rn(fa, C.w_ret) : __fdiv_rn(C.w_ret, S);
+      const double po = (double)fo, dpa = (double)fa - po, dpp = (double)fp - po;
 
       uint32_t choice = d;                                            // default: cdf[-1] < u (overflow)
       bool replay = (P.flags & B2W_FLAG_FORCE_EXACT_REPLAY) != 0;
       if (!replay) {
-        // word level: first word whose last position possibly reaches u
-        uint32_t carry = 0, wsel = NONE, bits_sel = 0, nc_before = 0;
-        for (uint32_t w0 = 0; w0 < nwords; w0 += G) {
-          const uint32_t w = w0 + T.tl;
-          const bool valid = w < nwords;
-          const uint32_t bits = (valid && has_prev) ? bm[w] : 0u;
-          const uint32_t cnt = __popc(bits);
-          const uint32_t incl = T.incl_scan(cnt) + carry;
-          const uint32_t kend = min(d, (w + 1) << 5) - 1;
-          const uint32_t hk = (kp <= kend) ? 1u : 0u;                 // NONE compares false
-          const double Tk = (double)incl * pa + (double)(kend + 1 - incl - hk) * po + (double)hk * pp;
-          const double hi_b = Tk + Tk * (EC * (double)(kend + 2));
-          const uint32_t bal = T.ballot(valid && (hi_b >= u));
-          if (bal) {
-            const int src = __ffs(bal) - 1;
-            wsel = w0 + src;
-            bits_sel = T.shfl(bits, src);
-            nc_before = T.shfl(incl - cnt, src);
-            break;
+        // T_k = (k+1) po + n_in(k) (pa - po) + [kp <= k] (pp - po), all in f64 (filter arithmetic only)
+        uint32_t wsel = 0, bits_sel = 0, nc_before = 0;
+        if (nwords > 1) {
+          // word level: first word whose last position possibly reaches u
+          uint32_t carry = 0;
+          wsel = NONE;
+          for (uint32_t w0 = 0; w0 < nwords; w0 += G) {
+            const uint32_t w = w0 + T.tl;
+            const bool valid = w < nwords;
+            const uint32_t bits = (valid && has_prev) ? bm[w] : 0u;
+            const uint32_t cnt = __popc(bits);
+            const uint32_t incl = T.incl_scan(cnt) + carry;
+            const uint32_t kend = min(d, (w + 1) << 5) - 1;
+            double Tk = fma((double)(kend + 1), po, (double)incl * dpa);
+            if (kp <= kend) Tk += dpp;                                // NONE compares false
+            const double hi_b = fma(Tk, EC * (double)(kend + 2), Tk);
+            const uint32_t bal = T.ballot(valid && (hi_b >= u));
+            if (bal) {
+              const int src = __ffs(bal) - 1;
+              wsel = w0 + src;
+              bits_sel = T.shfl(bits, src);
+              nc_before = T.shfl(incl - cnt, src);
+              break;
+            }
+            carry = T.shfl(incl, G - 1);
           }
-          carry = T.shfl(incl, G - 1);
+        } else if (has_prev) {
+          bits_sel = bm[0];
         }
         if (wsel != NONE) {
           // position level inside the selected word
           bool decided = false;
-#pragma unroll
-          for (int r = 0; r < 32 / G; ++r) {
-            const uint32_t b = r * G + T.tl;
+          const uint32_t nb = min(32u, d - (wsel << 5));
+          for (uint32_t r0 = 0; r0 < nb && !decided; r0 += G) {
+            const uint32_t b = r0 + T.tl;
             const uint32_t k = (wsel << 5) + b;
-            const bool valid = k < d;
-            const uint32_t nc = nc_before + __popc(bits_sel & (0xFFFFFFFFu >> (31 - b)));
-            const uint32_t hk = (kp <= k) ? 1u : 0u;
-            const double Tk = (double)nc * pa + (double)(k + 1 - nc - hk) * po + (double)hk * pp;
+            const bool valid = b < nb;
+            const uint32_t nc = nc_before + __popc(bits_sel & (0xFFFFFFFFu >> (31 - (b & 31))));
+            double Tk = fma((double)(k + 1), po, (double)nc * dpa);
+            if (kp <= k) Tk += dpp;
             const double Ek = Tk * (EC * (double)(k + 2));
             const uint32_t bp = T.ballot(valid && (Tk + Ek >= u));
-            if (!decided && bp) {
-              const int fp = __ffs(bp) - 1;
-              const bool sure = T.shfl((Tk - Ek >= u) ? 1 : 0, fp) != 0;
-              if (sure) choice = (wsel << 5) + r * G + fp; else replay = true;
+            if (bp) {
+              const int f = __ffs(bp) - 1;
+              const bool sure = T.shfl((Tk - Ek >= u) ? 1 : 0, f) != 0;
+              if (sure) choice = (wsel << 5) + r0 + f; else replay = true;
               decided = true;
             }
           }
@@ -242,33 +326,19 @@ __global__ void __launch_bounds__(UW_THREADS) walk_uw_kernel(const WalkParams P,
         }
       }
       if (replay) {
-        // ---------------- exact replay of the sequential f32 cumsum from the bitmap
-        const float fa = (float)pa, fo = (float)po, fp_ = (float)pp;
-        float cdf = 0.f;
-        choice = d;
-        uint32_t k = 0;
-        for (uint32_t w = 0; w < nwords && choice == d; ++w) {
-          const uint32_t bits = has_prev ? bm[w] : 0u;
-          const uint32_t nb = min(32u, d - (w << 5));
-          for (uint32_t b = 0; b < nb; ++b, ++k) {
-            float v = ((bits >> b) & 1u) ? fa : fo;
-            if (k == kp) v = fp_;
-            cdf = __fadd_rn(cdf, v);
-            if (!((double)cdf < u)) { choice = k; break; }
-          }
-        }
+        choice = replay_exact<G>(bm, has_prev, nwords, d, kp, fa, fo, fp, u);
         ++st_replays;
       }
       if (choice == d) ++st_overflow;
       T.sync();                                                       // bitmap is rewritten by the next step
 
-      const uint32_t nxt = __ldg(P.indices + cs + choice);            // unchecked, as pecanpy.py:559
+      const uint32_t nxt = __ldg(crow + choice);                      // unchecked, as pecanpy.py:559
       if (T.tl == (j & (G - 1))) myval = nxt;
       if ((j & (G - 1)) == G - 1) {
         out[(j & ~(uint32_t)(G - 1)) + T.tl] = myval;
         myval = 0u;
       }
-      prev = cur; ps = cs; pdeg = d;
+      prev = cur; prow = crow; pdeg = d;
       cur = nxt;
       cs = __ldg(P.indptr + cur);
       ce = __ldg(P.indptr + cur + 1);
@@ -352,6 +422,9 @@ int b2w_launch_uw(const b2w_graph* g, const WalkParams& P_in, cudaStream_t s) {
   UwConsts C;
   C.w_out = (float)(1.0 / P.q);
   C.w_ret = (float)(1.0 / P.p);
+  auto pow2 = [](float v) { int e; float mnt = frexpf(v, &e); return mnt == 0.5f && e >= -19 && e <= 21; };
+  C.out_pow2 = pow2(C.w_out) ? 1 : 0;
+  C.ret_pow2 = pow2(C.w_ret) ? 1 : 0;
   C.gbm = reinterpret_cast<uint32_t*>(base + 256);
   C.gbm_stride = gbm_stride(g);
   B2W_CUDA(cudaMemsetAsync(P.counter, 0, 8, s));
