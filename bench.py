@@ -39,6 +39,8 @@ WORKLOADS = {
     # name: (mode, p, q, extend, gamma, weighted, generator, n, m, num_walks, L)
     "powerlaw-1M-10M-sparseotf": dict(mode="SparseOTF", p=4.0, q=0.25, extend=False, gen="powerlaw", n=1_000_000,
                                       m=10_000_000, weighted=False, num_walks=10, L=80, seed=1),
+    "powerlaw-1M-10M-sparseotf-weighted": dict(mode="SparseOTF", p=4.0, q=0.25, extend=False, gen="powerlaw",
+                                               n=1_000_000, m=10_000_000, weighted=True, num_walks=10, L=80, seed=1),
     "er-100k-1M-sparseotf": dict(mode="SparseOTF", p=0.5, q=2.0, extend=False, gen="er", n=100_000, m=1_000_000,
                                  weighted=False, num_walks=10, L=80, seed=0),
     "er-50k-1M-precomp": dict(mode="PreComp", p=0.25, q=4.0, extend=False, gen="er", n=50_000, m=1_000_000,
@@ -188,11 +190,18 @@ def cpu_port_rate(wl, g, start, L, budget_s: float, seed: int):
         dt = time.perf_counter() - t0
         return int((out[:, -1].astype(np.int64) - 1).sum()), dt
 
-    probe = min(start.size, 2000 if g["kind"] != "dense" else 16)
-    s, dt = run(probe)
-    rate = s / max(dt, 1e-9)
-    rows = int(min(start.size, max(probe, rate * budget_s / max(L, 1))))
-    s, dt = run(rows)
+    # grow the sample until it runs for at least ~40% of the budget (thread start-up and cold caches make
+    # a tiny probe a poor predictor), capped by the budget and by the job size
+    rows = min(start.size, 4000 if g["kind"] != "dense" else 64)
+    while True:
+        s, dt = run(rows)
+        if dt >= 0.4 * budget_s or rows >= start.size:
+            break
+        rate = s / max(dt, 1e-9)
+        nxt = int(min(start.size, max(2 * rows, rate * budget_s / max(L, 1))))
+        if nxt <= rows:
+            break
+        rows = nxt
     return s / dt, cores, f"first {rows} rows of the shuffled start array x {L} steps ({s} steps in {dt:.2f}s)", rows
 
 

@@ -31,13 +31,13 @@
 #include <cmath>
 #include <cstring>
 
-#include "b2w_common.cuh"
+#include "b2w_membership.cuh"
 
 namespace {
 
 constexpr int UW_THREADS = 256;
 constexpr int UW_BW = 32;            // bitmap words of shared memory per group (rows up to 1024)
-constexpr uint32_t NONE = 0xFFFFFFFFu;
+constexpr uint32_t NONE = B2W_NONE;
 
 struct UwConsts {
   float w_out, w_ret;                // f32(1/q), f32(1/p)
@@ -45,56 +45,6 @@ struct UwConsts {
   uint32_t gbm_stride;               // words of global bitmap scratch per group (0: never needed)
   uint32_t* gbm;                     // global bitmap scratch
 };
-
-template <int G>
-struct Tile {
-  int lane, tl, base;
-  uint32_t mask;
-  __device__ __forceinline__ Tile() {
-    lane = threadIdx.x & 31;
-    tl = lane & (G - 1);
-    base = lane & ~(G - 1);
-    mask = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << base);
-  }
-  __device__ __forceinline__ uint32_t ballot(bool p) const {
-    uint32_t b = __ballot_sync(mask, p);
-    return (G == 32) ? b : ((b >> base) & ((1u << G) - 1u));
-  }
-  template <typename T>
-  __device__ __forceinline__ T shfl(T v, int src) const { return __shfl_sync(mask, v, src, G); }
-  __device__ __forceinline__ void sync() const { __syncwarp(mask); }
-  __device__ __forceinline__ uint32_t incl_scan(uint32_t v) const {
-#pragma unroll
-    for (int o = 1; o < G; o <<= 1) {
-      uint32_t t = __shfl_up_sync(mask, v, o, G);
-      if (tl >= o) v += t;
-    }
-    return v;
-  }
-  __device__ __forceinline__ uint32_t sum(uint32_t v) const {
-#pragma unroll
-    for (int o = G / 2; o; o >>= 1) v += __shfl_xor_sync(mask, v, o, G);
-    return v;
-  }
-  __device__ __forceinline__ uint32_t minu(uint32_t v) const {
-#pragma unroll
-    for (int o = G / 2; o; o >>= 1) v = min(v, __shfl_xor_sync(mask, v, o, G));
-    return v;
-  }
-};
-
-// Number of elements of the sorted row[0..n) that are < x.  Branch-free, `lg` = 32 - clz(n)
-// iterations (uniform across the group): pos only grows over a prefix of elements < x.
-__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__ row, uint32_t n, uint32_t x,
-                                                    uint32_t lg) {
-  uint32_t pos = 0;
-  for (uint32_t step = lg ? (1u << (lg - 1)) : 0u; step; step >>= 1) {
-    const uint32_t idx = pos + step;
-    const uint32_t v = __ldg(row + (min(idx, n) - 1));
-    if (idx <= n && v < x) pos = idx;
-  }
-  return pos;
-}
 
 __device__ __forceinline__ double pow2_double(int e) { return __hiloint2double((1023 + e) << 20, 0); }
 
@@ -174,8 +124,8 @@ __device__ __noinline__ uint32_t replay_exact(const uint32_t* __restrict__ bm, c
   return d;                                                           // cdf[-1] < u: the reference's overflow
 }
 
-template <int G>
-__global__ void __launch_bounds__(UW_THREADS) walk_uw_kernel(const WalkParams P, const UwConsts C) {
+template <int G, int MINB>
+__global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_kernel(const WalkParams P, const UwConsts C) {
   constexpr int GROUPS = UW_THREADS / G;
   __shared__ uint32_t s_bm[GROUPS][UW_BW];
   const Tile<G> T;
@@ -216,48 +166,7 @@ __global__ void __launch_bounds__(UW_THREADS) walk_uw_kernel(const WalkParams P,
 
       // ---------------- phase 1: membership bitmap over the positions of row(cur)
       uint32_t m = 0, kp = NONE;
-      if (has_prev) {
-        const uint32_t lgp = 32 - __clz(pdeg), lgd = 32 - __clz(d);
-        const uint32_t fwd_cost = ((d + G - 1) / G) * (lgp + 2);
-        const uint32_t rev_cost = ((pdeg + G) / G) * (lgd + 2) + (nwords + G - 1) / G;
-        if (fwd_cost <= rev_cost) {
-          // every neighbour of cur looked up in row(prev); each bitmap word is written, none needs clearing
-          for (uint32_t c0 = 0; c0 < d; c0 += G) {
-            const uint32_t k = c0 + T.tl;
-            const bool valid = k < d;
-            const uint32_t x = valid ? __ldg(crow + k) : NONE;
-            const uint32_t pos = lower_bound_u32(prow, pdeg, x, lgp);
-            const bool found = pos < pdeg && __ldg(prow + pos) == x;
-            const bool isprev = valid && (x == prev);
-            const uint32_t bprev = T.ballot(isprev);
-            if (bprev) kp = c0 + __ffs(bprev) - 1;
-            const uint32_t bal = T.ballot(valid && found && !isprev);
-            if (T.tl == 0) {
-              if (G == 32 || (c0 & 31) == 0) bm[c0 >> 5] = bal; else bm[c0 >> 5] |= bal << (c0 & 31);
-            }
-            m += __popc(bal);
-          }
-        } else {
-          // every neighbour of prev (and prev itself, last key) looked up in row(cur)
-          for (uint32_t w = T.tl; w < nwords; w += G) bm[w] = 0u;
-          T.sync();
-          const uint32_t nkeys = pdeg + 1;
-          uint32_t mloc = 0, kploc = NONE;
-          for (uint32_t c0 = 0; c0 < nkeys; c0 += G) {
-            const uint32_t ii = c0 + T.tl;
-            const bool valid = ii < nkeys;
-            const uint32_t y = valid ? (ii < pdeg ? __ldg(prow + ii) : prev) : NONE;
-            const uint32_t pos = lower_bound_u32(crow, d, y, lgd);
-            if (valid && pos < d && __ldg(crow + pos) == y) {
-              if (ii == pdeg) kploc = pos;
-              else if (y != prev) { atomicOr(&bm[pos >> 5], 1u << (pos & 31)); ++mloc; }
-            }
-          }
-          m = T.sum(mloc);
-          kp = T.minu(kploc);
-        }
-        T.sync();
-      }
+      if (has_prev) m = membership_bitmap<G>(T, crow, d, prow, pdeg, prev, bm, kp);
 
       // ---------------- phase 2: exact normaliser, three-valued probabilities
       const float w_o = has_prev ? C.w_out : 1.0f;                    // first step: every weight is 1
@@ -360,10 +269,10 @@ __global__ void __launch_bounds__(UW_THREADS) walk_uw_kernel(const WalkParams P,
   }
 }
 
-template <int G>
+template <int G, int MINB>
 int grid_blocks(const b2w_graph* g) {
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, walk_uw_kernel<G>, UW_THREADS, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, walk_uw_kernel<G, MINB>, UW_THREADS, 0);
   if (per_sm < 1) per_sm = 1;
   return per_sm * g->num_sms;
 }
@@ -376,9 +285,7 @@ int pick_group(const b2w_graph* g, uint32_t flags) {
 }
 
 uint32_t max_groups(const b2w_graph* g) {
-  int b8 = grid_blocks<8>(g), b16 = grid_blocks<16>(g), b32 = grid_blocks<32>(g);
-  uint32_t a = (uint32_t)b8 * (UW_THREADS / 8), b = (uint32_t)b16 * (UW_THREADS / 16), c = (uint32_t)b32 * (UW_THREADS / 32);
-  return max(a, max(b, c));
+  return (uint32_t)g->num_sms * 8u * (UW_THREADS / 8);               // upper bound: 8 resident CTAs of 8-lane groups
 }
 
 uint32_t gbm_stride(const b2w_graph* g) {
@@ -429,12 +336,18 @@ int b2w_launch_uw(const b2w_graph* g, const WalkParams& P_in, cudaStream_t s) {
   C.gbm_stride = gbm_stride(g);
   B2W_CUDA(cudaMemsetAsync(P.counter, 0, 8, s));
   const int G = pick_group(g, P.flags);
-  int blocks = G == 8 ? grid_blocks<8>(g) : (G == 16 ? grid_blocks<16>(g) : grid_blocks<32>(g));
+  const int MB = (int)((P.flags >> 16) & 0xF);                        // tuning: min resident CTAs per SM (0 = default)
   uint64_t groups_per_block = UW_THREADS / G;
   uint64_t need = (P.n_rows + groups_per_block - 1) / groups_per_block;
-  if ((uint64_t)blocks > need) blocks = (int)(need ? need : 1);
-  if (G == 8) walk_uw_kernel<8><<<blocks, UW_THREADS, 0, s>>>(P, C);
-  else if (G == 16) walk_uw_kernel<16><<<blocks, UW_THREADS, 0, s>>>(P, C);
-  else walk_uw_kernel<32><<<blocks, UW_THREADS, 0, s>>>(P, C);
+#define B2W_UW_LAUNCH(GG, BB)                                                        \
+  do {                                                                               \
+    int blocks = grid_blocks<GG, BB>(g);                                             \
+    if ((uint64_t)blocks > need) blocks = (int)(need ? need : 1);                    \
+    walk_uw_kernel<GG, BB><<<blocks, UW_THREADS, 0, s>>>(P, C);                      \
+  } while (0)
+  if (G == 8) B2W_UW_LAUNCH(8, 4);
+  else if (G == 16) { if (MB == 4) B2W_UW_LAUNCH(16, 4); else if (MB == 6) B2W_UW_LAUNCH(16, 6); else B2W_UW_LAUNCH(16, 5); }
+  else { if (MB == 4) B2W_UW_LAUNCH(32, 4); else if (MB == 6) B2W_UW_LAUNCH(32, 6); else B2W_UW_LAUNCH(32, 5); }   // measured: 5 CTAs/SM (48 regs) best
+#undef B2W_UW_LAUNCH
   return b2w_cuda_fail(cudaGetLastError(), "walk_uw_kernel launch");
 }

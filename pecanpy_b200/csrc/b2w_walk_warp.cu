@@ -1,202 +1,206 @@
-// b2w_walk_warp.cu -- SparseOTF: one warp per walker, persistent CTAs, dynamic row queue.
+// b2w_walk_warp.cu -- generic SparseOTF (weighted graphs, node2vec+, any p and q): one warp per
+// walker, persistent CTAs, dynamic row queue.
 //
-// Per step the warp streams row(cur) (indices + weights) with coalesced loads, resolves
-// membership of every neighbour in row(prev) by a lane-parallel binary search, forms the biased
-// weights, and must then reproduce -- bit for bit -- the reference's
+// Per step the warp must reproduce -- bit for bit -- the reference's
 //     probs = w / w.sum();  cdf = np.cumsum(probs);  choice = np.searchsorted(cdf, u)
-// (pecanpy.py:546-559, rw/sparse_rw.py:51-130) whose sum and cumsum are SEQUENTIAL f32
-// recurrences (numba/np/arraymath.py:161-174, :384-405).  A warp scan re-associates, so it is
-// used as a FILTER with a rigorous error bound, never as the answer:
+// (pecanpy.py:546-559, rw/sparse_rw.py:51-130) whose sum and cumsum are SEQUENTIAL f32 recurrences
+// (numba/np/arraymath.py:161-174, :384-405).  Parallel arithmetic is used as a FILTER with a rigorous
+// error bound, never as the answer:
 //
-//  (1) normaliser S.  If every weight is a multiple of one power of two g and the total is
-//      below 2^24 g, no f32 partial sum in ANY order can round, so the exact f64 warp reduction
-//      equals the sequential f32 sum (checked per step; always true for unweighted graphs with
-//      power-of-two p, q).  Otherwise S is accumulated sequentially from shared memory.
-//  (2) probs_k = fdiv_rn(w_k, S) elementwise -- exact.
-//  (3) cdf.  A_k = warp-scan prefix (f32).  Both the reference's sequential prefix and A_k are
-//      floating-point summations of the same non-negative terms, so each is within
-//      gamma_m * T_k of the exact prefix T_k (m = number of additions on the longest path):
-//      |cdf_k - A_k| <= E_k := (k + chunk + 8) * 1.01 * 2^-24 * A_k.  If the first k with
-//      A_k + E_k >= u also satisfies A_k - E_k >= u, then choice = k, provably.  Otherwise
-//      (probability ~ deg^2 * 4e-8 per step) the warp replays the f32 recurrence exactly.
+//  phase 1  (node2vec) membership bitmap of N(cur) & N(prev) over the positions of row(cur), searching
+//           the cheaper side (b2w_membership.cuh); (node2vec+) per-element lower_bound in row(prev),
+//           because each common neighbour also needs w(prev, x) / thr[x].
+//  phase 2  stream the weights of row(cur) once (coalesced), form the biased weights w_k, stage them
+//           in shared memory (rows above 1020 entries: a per-warp scratch row that stays in L2) and
+//           keep one f32 partial sum per 32-element chunk.
+//  filter   Let P_k be the exact prefix sums of w.  The reference computes S = fl-sum(w) (relative error
+//           gamma_{d-1}), probs_k = fl(w_k / S) (2^-24 each) and cdf_k = fl-cumsum (gamma_k); all terms are
+//           non-negative, so cdf_k = (P_k / P_{d-1}) (1 +- (gamma_k + gamma_{d-1} + 2^-24)).  The warp's own
+//           chunk totals / scans are float summations of the same terms with depth <= nchunks + 12.
+//           Hence |cdf_k - A_k / T| <= e_k A_k / T with e_k = (k + d + 2 nchunks + 40) 1.01 2^-24, and the
+//           first k with A_k (1 + e_k) >= u T is the reference's choice whenever A_k (1 - e_k) >= u T.
+//  replay   otherwise (probability ~ d^2 1e-7 per step) the warp re-runs the reference's recurrences
+//           exactly: sequential f32 sum, fdiv per element, sequential f32 cumsum (float4 broadcast reads).
 //
 // Reference: pecanpy.py:164-210 (_random_walks), :522-561 (SparseOTF.get_move_forward).
-#include "b2w_common.cuh"
+#include "b2w_membership.cuh"
 
 namespace {
 
 constexpr int WARPS_PER_CTA = 8;
-constexpr int CAP = 1024;   // floats of shared memory per warp (rows above this use global scratch)
+constexpr int CAP = 1024;   // staged weights per warp in shared memory (longer rows use global scratch)
 
-__device__ __forceinline__ double warp_sum_f64(double v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(B2W_FULL, v, o));
-  return v;
-}
+struct __align__(16) WarpBuf {
+  float w[CAP];
+  float ctot[CAP / 32];
+  uint32_t bm[CAP / 32];
+};
 
 struct WarpStats { uint32_t steps, replays, seqsums, overflow; };
 
+__device__ __forceinline__ float warp_sum_f32(float v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(B2W_FULL, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float warp_incl_scan_f32(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_up_sync(B2W_FULL, v, o);
+    if (lane >= o) v = __fadd_rn(v, t);
+  }
+  return v;
+}
+
 template <bool EXTEND>
-__device__ __forceinline__ uint32_t otf_choice_warp(const WalkParams& P, const int lane, const uint32_t cur,
-                                                    const uint32_t cs, const uint32_t deg, const bool has_prev,
+__device__ __forceinline__ uint32_t otf_choice_warp(const WalkParams& P, const Tile<32>& T, const uint32_t cur,
+                                                    const uint32_t cs, const uint32_t d, const bool has_prev,
                                                     const uint32_t prev, const uint32_t ps, const uint32_t pdeg,
-                                                    const double u, float* __restrict__ wbuf, WarpStats& st) {
-  const uint32_t nchunks = (deg + 31) >> 5;
-  const uint32_t nit = has_prev ? (32 - __clz(pdeg)) : 0;   // lower_bound iterations for pdeg elements
+                                                    const double u, float* __restrict__ wbuf,
+                                                    float* __restrict__ ctot, uint32_t* __restrict__ bm,
+                                                    WarpStats& st) {
+  const int lane = T.lane;
+  const uint32_t nchunks = (d + 31) >> 5;
+  const uint32_t* const crow = P.indices + cs;
+  const float* const cdat = P.data + cs;
+  const uint32_t* const prow = P.indices + ps;
+  const float* const pdat = P.data + ps;
+
+  // ---- phase 1: membership (node2vec)
+  uint32_t kp = B2W_NONE;
+  if (!EXTEND && has_prev) membership_bitmap<32>(T, crow, d, prow, pdeg, prev, bm, kp);
+
+  // ---- phase 2: stream the weights, stage w, one partial sum per chunk
+  const uint32_t lgp = 32 - __clz(pdeg);
   float thr_cur = 0.f;
   if (EXTEND && has_prev) thr_cur = __ldg(P.thr + cur);
-
-  // ---- pass A: biased weights -> wbuf, exactness statistics for the normaliser
-  double acc = 0.0;
-  unsigned long long orbits = 0ull;
-  bool bad = false;
+  float total = 0.f;
   for (uint32_t c = 0; c < nchunks; ++c) {
     const uint32_t k = (c << 5) + lane;
-    const bool valid = k < deg;
-    uint32_t x = 0xFFFFFFFFu;
-    float wt = 0.f;
-    if (valid) { x = __ldg(P.indices + cs + k); wt = __ldg(P.data + cs + k); }
+    const bool valid = k < d;
+    const float wt = valid ? __ldg(cdat + k) : 0.f;
     float w = wt;
     if (has_prev) {
-      uint32_t lo = 0, hi = pdeg;
-      bool common = false;
-      for (uint32_t it = 0; it < nit; ++it) {
-        if (lo < hi) {
-          uint32_t mid = (lo + hi) >> 1;
-          uint32_t v = __ldg(P.indices + ps + mid);
-          common |= (v == x);
-          if (v < x) lo = mid + 1; else hi = mid;
-        }
-      }
-      if (valid) {
-        if (x == prev) {
-          w = div_by(wt, P.p, P.invp_f, P.p_pow2);                     // return bias (sparse_rw.py:87/126)
-        } else if (!EXTEND) {
-          if (!common) w = div_by(wt, P.q, P.invq_f, P.q_pow2);        // out bias (:86)
-        } else {
-          bool out = true;
-          float t = 0.f;
-          if (common) {
-            float wp = __ldg(P.data + ps + lo);
-            float th = __ldg(P.thr + x);
-            if (wp >= th) out = false; else t = __fdiv_rn(wp, th);     // (:273-276)
-          }
-          if (out) {
-            double alpha = __dadd_rn(P.invq, __dmul_rn(__dsub_rn(1.0, P.invq), (double)t));   // (:119)
-            if (wt < thr_cur) alpha = P.supp;                          // (:122-124)
-            w = (float)__dmul_rn((double)wt, alpha);                   // (:125)
+      if (!EXTEND) {
+        const uint32_t bits = bm[c];
+        if (k == kp) w = div_by(wt, P.p, P.invp_f, P.p_pow2);                  // return bias (sparse_rw.py:87)
+        else if (!((bits >> lane) & 1u)) w = div_by(wt, P.q, P.invq_f, P.q_pow2);   // out bias (:86)
+      } else {
+        const uint32_t x = valid ? __ldg(crow + k) : B2W_NONE;
+        const uint32_t pos = lower_bound_u32(prow, pdeg, x, lgp);
+        const bool common = pos < pdeg && __ldg(prow + pos) == x;
+        if (valid) {
+          if (x == prev) {
+            w = div_by(wt, P.p, P.invp_f, P.p_pow2);                           // (:126)
+          } else {
+            bool out = true;
+            float t = 0.f;
+            if (common) {
+              const float wp = __ldg(pdat + pos);
+              const float th = __ldg(P.thr + x);
+              if (wp >= th) out = false; else t = __fdiv_rn(wp, th);           // (:273-276)
+            }
+            if (out) {
+              double alpha = __dadd_rn(P.invq, __dmul_rn(__dsub_rn(1.0, P.invq), (double)t));   // (:119)
+              if (wt < thr_cur) alpha = P.supp;                                // (:122-124)
+              w = (float)__dmul_rn((double)wt, alpha);                         // (:125)
+            }
           }
         }
       }
     }
-    if (valid) {
-      wbuf[k] = w;
-      double wd = (double)w;
-      acc = __dadd_rn(acc, wd);
-      // multiples of 2^-40 below 2^13 keep every f64 partial sum exact (53 bits)
-      if (w == 0.f || (w >= 7.62939453125e-06f && w < 8192.f))
-        orbits |= (unsigned long long)__double2ll_rn(wd * 1099511627776.0);
-      else
-        bad = true;
-    }
+    if (valid) wbuf[k] = w; else w = 0.f;
+    const float tot = warp_sum_f32(w);
+    if (lane == 0) ctot[c] = tot;
+    total = __fadd_rn(total, tot);
   }
-  // zero pad to a multiple of 4 for the float4 replay reads
-  if (lane < 4) {
-    uint32_t k = deg + lane;
-    if (k < ((deg + 3) & ~3u)) wbuf[k] = 0.f;
+  if (lane < 4) {                                                               // zero pad for float4 replay reads
+    const uint32_t k = d + lane;
+    if (k < ((d + 3) & ~3u)) wbuf[k] = 0.f;
   }
   __syncwarp();
 
-  // ---- normaliser S (sequential f32 sum of the reference)
-  const double T = warp_sum_f64(acc);
-  const uint32_t or_lo = __reduce_or_sync(B2W_FULL, (uint32_t)orbits);
-  const uint32_t or_hi = __reduce_or_sync(B2W_FULL, (uint32_t)(orbits >> 32));
-  const bool anybad = __any_sync(B2W_FULL, bad);
-  float S;
-  bool exactS = false;
-  if (!anybad && T < 8192.0 && T > 0.0) {
-    int tz = or_lo ? (__ffs(or_lo) - 1) : (32 + __ffs(or_hi) - 1);
-    // all weights are multiples of g = 2^(tz-40); exact if T < 2^24 * g
-    double lim = scalbn(1.0, 24 + tz - 40);
-    exactS = T < lim;
-  }
-  const uint32_t n4 = (deg + 3) >> 2;
-  const float4* w4 = reinterpret_cast<const float4*>(wbuf);
-  if (exactS) {
-    S = (float)T;
-  } else {
-    float s = 0.f;
-    for (uint32_t i = 0; i < n4; ++i) {
-      float4 v = w4[i];
-      s = __fadd_rn(s, v.x); s = __fadd_rn(s, v.y); s = __fadd_rn(s, v.z); s = __fadd_rn(s, v.w);
-    }
-    S = s;
-    st.seqsums++;
-  }
-
-  // ---- cdf: warp-scan filter
-  const bool force = (P.flags & B2W_FLAG_FORCE_EXACT_REPLAY) || !(S > 0.f) || !(S < 3.0e38f) || deg > (1u << 20);
-  uint32_t choice = deg;       // default: no k with cdf_k >= u -> the reference's choice == deg overflow
-  bool replay = force;
-  uint32_t c = 0;
-  if (!force) {
-    float carry = 0.f;
-    for (; c < nchunks; ++c) {
-      const uint32_t k = (c << 5) + lane;
-      const bool valid = k < deg;
-      float pr = 0.f;
-      if (valid) { pr = __fdiv_rn(wbuf[k], S); wbuf[k] = pr; }
-      float a = pr;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        float t = __shfl_up_sync(B2W_FULL, a, o);
-        if (lane >= o) a = __fadd_rn(a, t);
-      }
-      const float A = __fadd_rn(carry, a);
-      const float E = __fmul_rn(__fmul_rn((float)(k + c + 8), 6.0201e-08f), A);   // 1.01 * 2^-24
-      const double lo_b = (double)A - (double)E, hi_b = (double)A + (double)E;
-      const uint32_t bp = __ballot_sync(B2W_FULL, valid && (hi_b >= u));   // possibly  cdf_k >= u
-      if (bp) {
-        const uint32_t bd = __ballot_sync(B2W_FULL, valid && (lo_b >= u)); // certainly cdf_k >= u
-        const int fp = __ffs(bp) - 1;
-        if (bd && (__ffs(bd) - 1) == fp) choice = (c << 5) + fp; else replay = true;
-        ++c;   // chunk c has been converted to probabilities
+  // ---- filter in the un-normalised domain: compare prefix sums with u * total
+  uint32_t choice = d;                       // default: every bound below u -> the reference's choice == deg
+  bool replay = (P.flags & B2W_FLAG_FORCE_EXACT_REPLAY) || !(total > 0.f) || !(total < 3.0e38f) || d > (1u << 20);
+  if (!replay) {
+    const double uT = u * (double)total;
+    const double EC = 1.01 * 5.9604644775390625e-08;
+    const double ebase = (double)(d + 2 * nchunks + 40);
+    float carry = 0.f, excl_sel = 0.f;
+    uint32_t csel = B2W_NONE;
+    for (uint32_t c0 = 0; c0 < nchunks; c0 += 32) {
+      const uint32_t c = c0 + lane;
+      const bool valid = c < nchunks;
+      const float v = valid ? ctot[c] : 0.f;
+      const float incl = __fadd_rn(carry, warp_incl_scan_f32(v, lane));
+      const uint32_t kend = min(d, (c + 1) << 5) - 1;
+      const double A = (double)incl;
+      const uint32_t bal = __ballot_sync(B2W_FULL, valid && (fma(A, EC * (ebase + (double)kend), A) >= uT));
+      if (bal) {
+        const int src = __ffs(bal) - 1;
+        csel = c0 + src;
+        const float up = __shfl_up_sync(B2W_FULL, incl, 1);
+        excl_sel = __shfl_sync(B2W_FULL, lane == 0 ? carry : up, src);
         break;
       }
-      carry = __shfl_sync(B2W_FULL, A, 31);
+      carry = __shfl_sync(B2W_FULL, incl, 31);
+    }
+    if (csel != B2W_NONE) {
+      const uint32_t k = (csel << 5) + lane;
+      const bool valid = k < d;
+      const float w = valid ? wbuf[k] : 0.f;
+      const double A = (double)__fadd_rn(excl_sel, warp_incl_scan_f32(w, lane));
+      const double E = A * (EC * (ebase + (double)k));
+      const uint32_t bp = __ballot_sync(B2W_FULL, valid && (A + E >= uT));
+      if (bp) {
+        const int f = __ffs(bp) - 1;
+        const bool sure = __shfl_sync(B2W_FULL, (A - E >= uT) ? 1 : 0, f) != 0;
+        if (sure) choice = (csel << 5) + f; else replay = true;
+      } else {
+        replay = true;                                                          // rounding at the chunk boundary
+      }
     }
   }
   if (replay) {
-    // ---- exact replay of the f32 recurrence
-    for (; c < nchunks; ++c) {
-      const uint32_t k = (c << 5) + lane;
-      if (k < deg) wbuf[k] = __fdiv_rn(wbuf[k], S);
-    }
-    __syncwarp();
-    float cdf = 0.f;
-    choice = deg;
+    // ---- exact replay of the reference's recurrences
+    const uint32_t n4 = (d + 3) >> 2;
+    const float4* w4 = reinterpret_cast<const float4*>(wbuf);
+    float s = 0.f;
     for (uint32_t i = 0; i < n4; ++i) {
-      float4 v = w4[i];
-      cdf = __fadd_rn(cdf, v.x); if (!((double)cdf < u)) { choice = 4 * i; break; }
-      cdf = __fadd_rn(cdf, v.y); if (!((double)cdf < u)) { choice = 4 * i + 1; break; }
-      cdf = __fadd_rn(cdf, v.z); if (!((double)cdf < u)) { choice = 4 * i + 2; break; }
-      cdf = __fadd_rn(cdf, v.w); if (!((double)cdf < u)) { choice = 4 * i + 3; break; }
+      const float4 v = w4[i];
+      s = __fadd_rn(s, v.x); s = __fadd_rn(s, v.y); s = __fadd_rn(s, v.z); s = __fadd_rn(s, v.w);
     }
-    if (choice > deg) choice = deg;   // a hit on a zero pad element means cdf[deg-1] < u was false earlier
+    float cdf = 0.f;
+    choice = d;
+    for (uint32_t i = 0; i < n4; ++i) {
+      const float4 v = w4[i];
+      cdf = __fadd_rn(cdf, __fdiv_rn(v.x, s)); if (!((double)cdf < u)) { choice = 4 * i; break; }
+      cdf = __fadd_rn(cdf, __fdiv_rn(v.y, s)); if (!((double)cdf < u)) { choice = 4 * i + 1; break; }
+      cdf = __fadd_rn(cdf, __fdiv_rn(v.z, s)); if (!((double)cdf < u)) { choice = 4 * i + 2; break; }
+      cdf = __fadd_rn(cdf, __fdiv_rn(v.w, s)); if (!((double)cdf < u)) { choice = 4 * i + 3; break; }
+    }
+    if (choice > d) choice = d;
     st.replays++;
+    st.seqsums++;
   }
-  if (choice == deg) st.overflow++;
+  if (choice == d) st.overflow++;
   __syncwarp();
   return choice;
 }
 
 template <bool EXTEND>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32) walk_sparse_warp_kernel(const WalkParams P) {
-  __shared__ __align__(16) float smem_w[WARPS_PER_CTA][CAP];
+  __shared__ WarpBuf sbuf[WARPS_PER_CTA];
+  const Tile<32> T;
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const uint32_t warp_gid = blockIdx.x * WARPS_PER_CTA + wib;
-  float* gbuf = P.work + (size_t)warp_gid * P.work_stride;
+  // global scratch row of this warp: [w: work_stride floats][ctot: work_stride/32][bitmap: work_stride/32]
+  float* const gw = P.work + (size_t)warp_gid * (P.work_stride + 2 * (P.work_stride / 32));
+  float* const gctot = gw + P.work_stride;
+  uint32_t* const gbm = reinterpret_cast<uint32_t*>(gctot + P.work_stride / 32);
   const uint32_t L = P.L;
   WarpStats st = {0, 0, 0, 0};
 
@@ -224,8 +228,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32) walk_sparse_warp_kernel(co
         if (sj <= L) my_u = step_uniform(P, i, sj);
       }
       const double u = __shfl_sync(B2W_FULL, my_u, (j - 1) & 31);
-      float* wbuf = (deg + 4 <= CAP) ? smem_w[wib] : gbuf;
-      const uint32_t choice = otf_choice_warp<EXTEND>(P, lane, cur, cs, deg, j > 1, prev, ps, pdeg, u, wbuf, st);
+      const bool small = deg + 4 <= CAP;
+      const uint32_t choice = otf_choice_warp<EXTEND>(P, T, cur, cs, deg, j > 1, prev, ps, pdeg, u,
+                                                      small ? sbuf[wib].w : gw, small ? sbuf[wib].ctot : gctot,
+                                                      small ? sbuf[wib].bm : gbm, st);
       const uint32_t nxt = __ldg(P.indices + cs + choice);            // unchecked, as pecanpy.py:559
       if (lane == (j & 31)) myval = nxt;
       if ((j & 31) == 31) {                                           // entries [j-31, j] complete: flush
@@ -274,8 +280,8 @@ uint32_t b2w_sparse_warp_total_warps(const b2w_graph* g) {
 
 size_t b2w_sparse_warp_work_bytes(const b2w_graph* g) {
   // [0,256): row-queue counter; then one scratch row per resident warp for degrees above CAP-4
-  size_t stride = (g->max_degree + 4 > (uint32_t)CAP) ? (((size_t)g->max_degree + 4 + 3) & ~(size_t)3) : 0;
-  return 256 + (size_t)b2w_sparse_warp_total_warps(g) * stride * sizeof(float);
+  size_t stride = (g->max_degree + 4 > (uint32_t)CAP) ? (((size_t)g->max_degree + 4 + 127) & ~(size_t)127) : 0;
+  return 256 + (size_t)b2w_sparse_warp_total_warps(g) * (stride + 2 * (stride / 32)) * sizeof(float);
 }
 
 int b2w_launch_sparse_warp(const b2w_graph* g, const WalkParams& P_in, cudaStream_t s) {
@@ -283,7 +289,7 @@ int b2w_launch_sparse_warp(const b2w_graph* g, const WalkParams& P_in, cudaStrea
   char* base = reinterpret_cast<char*>(P_in.work);
   P.counter = reinterpret_cast<unsigned long long*>(base);
   P.work = reinterpret_cast<float*>(base + 256);
-  P.work_stride = (g->max_degree + 4 > (uint32_t)CAP) ? (uint32_t)(((size_t)g->max_degree + 4 + 3) & ~(size_t)3) : 0;
+  P.work_stride = (g->max_degree + 4 > (uint32_t)CAP) ? (uint32_t)(((size_t)g->max_degree + 4 + 127) & ~(size_t)127) : 0;
   B2W_CUDA(cudaMemsetAsync(P.counter, 0, 8, s));
   const bool extend = P.extend != 0;
   int grid = extend ? grid_for<true>(g) : grid_for<false>(g);
