@@ -351,6 +351,13 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_total, t_kernel_max = float(tt[0]), float(tt[1])
 
+    # kernel-side counters of one extra (untimed) pass: exact replays, reference-overflow choices
+    walk_stats = None
+    if my_rows and rank == 0:
+        eng.walk(wl["mode"], wl["p"], wl["q"], d_start, L, seed=K - 1 if K else 0, extend=wl["extend"], row0=lo,
+                 out=mine, flags=args.flags, collect_stats=True)
+        walk_stats = eng.stats()
+
     # steps of the whole job, from the last timed pass (every rank holds the full matrix when world > 1)
     steps_job = eng.count_steps(full[:tot] if world > 1 else mine[:my_rows], L)
     steps_mine = eng.count_steps(mine[:my_rows], L) if my_rows else 0
@@ -428,7 +435,7 @@ def main():
                 "vs_baseline": None, "dtype": dtype_of(wl), "data": "synthetic",
                 "config": config_of(args, wl, g, world), "clocks": clocks, "gpu_launches": K * (1 if my_rows else 0),
                 "steps_per_pass": steps_job, "kernel_ms_max_over_ranks": 1e3 * t_kernel_max / max(K, 1),
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e}
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "walk_stats_rank0": walk_stats}
         line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -281,7 +281,9 @@ int pick_group(const b2w_graph* g, uint32_t flags) {
   uint32_t forced = (flags >> 8) & 0xFF;                             // debug/tuning: bits 8..15 = group size
   if (forced == 8 || forced == 16 || forced == 32) return (int)forced;
   double avg = g->n ? (double)g->nnz / g->n : 0.0;
-  return avg <= 10.0 ? 16 : 32;   // measured: G=32 wins on power-law hubs, ties G=16 on ER(20)
+  // measured (B200): 16 lanes per walker win on flat low-degree graphs (ER, deg 20: 3.29 vs 2.99 G steps/s),
+  // 32 lanes win as soon as there are hub rows (power law: 1.77 vs 1.44)
+  return (avg <= 32.0 && (double)g->max_degree <= 8.0 * avg + 16.0) ? 16 : 32;
 }
 
 uint32_t max_groups(const b2w_graph* g) {

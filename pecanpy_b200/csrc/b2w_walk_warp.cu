@@ -172,14 +172,22 @@ __device__ __forceinline__ uint32_t otf_choice_warp(const WalkParams& P, const T
       const float4 v = w4[i];
       s = __fadd_rn(s, v.x); s = __fadd_rn(s, v.y); s = __fadd_rn(s, v.z); s = __fadd_rn(s, v.w);
     }
+    // probabilities in place, one fdiv per lane per chunk (a 0/0 on an all-zero row gives the reference's NaN)
+    for (uint32_t c = 0; c < nchunks; ++c) {
+      const uint32_t k = (c << 5) + lane;
+      if (k < d) wbuf[k] = __fdiv_rn(wbuf[k], s);
+    }
+    __syncwarp();
     float cdf = 0.f;
     choice = d;
     for (uint32_t i = 0; i < n4; ++i) {
       const float4 v = w4[i];
-      cdf = __fadd_rn(cdf, __fdiv_rn(v.x, s)); if (!((double)cdf < u)) { choice = 4 * i; break; }
-      cdf = __fadd_rn(cdf, __fdiv_rn(v.y, s)); if (!((double)cdf < u)) { choice = 4 * i + 1; break; }
-      cdf = __fadd_rn(cdf, __fdiv_rn(v.z, s)); if (!((double)cdf < u)) { choice = 4 * i + 2; break; }
-      cdf = __fadd_rn(cdf, __fdiv_rn(v.w, s)); if (!((double)cdf < u)) { choice = 4 * i + 3; break; }
+      const float c0 = __fadd_rn(cdf, v.x), c1 = __fadd_rn(c0, v.y), c2 = __fadd_rn(c1, v.z), c3 = __fadd_rn(c2, v.w);
+      if (!((double)c3 < u)) {                                                  // cdf is non-decreasing (or NaN)
+        choice = 4 * i + (!((double)c0 < u) ? 0 : !((double)c1 < u) ? 1 : !((double)c2 < u) ? 2 : 3);
+        break;
+      }
+      cdf = c3;
     }
     if (choice > d) choice = d;
     st.replays++;
