@@ -7,7 +7,8 @@
 // rw/dense_rw.py:34-118).  Here the row is cut into 128-column super tiles; pass 1 leaves one
 // f64 partial sum per super tile in shared memory, a warp scan over those finds the super tile
 // in which the prefix crosses u * total, and pass 2 re-reads only that super tile (L1/L2 hot) to
-// pick the column.  As in the sparse kernel the parallel sums are a FILTER: every quantity is
+// pick the column.  Each lane owns 4 adjacent columns of a super tile: one 32-bit mask load and two
+// 16-byte loads per f64 row (1 KiB contiguous per warp instruction).  As in the sparse kernel the parallel sums are a FILTER: every quantity is
 // within (2N + 256) * 2^-53 (relative) of the reference's sequentially rounded value, so the
 // choice is proven unless u falls inside that window around a boundary (probability ~1e-8 per
 // step), in which case one lane replays the reference's recurrences exactly.
@@ -23,26 +24,89 @@ constexpr int DWARPS = 8;
 constexpr int DTHREADS = DWARPS * 32;
 constexpr int SUPER = 128;   // columns per super tile (4 per lane)
 
+// One lane's share of a 128-column super tile: 4 ADJACENT columns k0 .. k0+3 (k0 = 128 t + 4 lane), so the
+// mask is one 32-bit load and each f64 row contributes two 16-byte loads per lane (1 KiB contiguous per warp
+// instruction).  VEC requires N % 4 == 0 (then every row base is 32-byte aligned); otherwise scalar loads.
+struct LaneTile {
+  double w[4];        // biased, un-normalised weights (0 for non-neighbours)
+  uint32_t nzmask;    // bit r set <=> column k0 + r is a neighbour of cur
+};
+
 template <bool EXTEND>
-__device__ __forceinline__ double dense_weight(const WalkParams& P, const double* __restrict__ rcur,
-                                               const double* __restrict__ rprev, const uint8_t* __restrict__ nzprev,
-                                               bool has_prev, uint32_t prev, uint32_t k, double thr_cur) {
-  double w = __ldg(rcur + k);
+__device__ __forceinline__ double dense_weight(const WalkParams& P, double w, const bool has_prev, const bool isprev,
+                                               const bool nzp, const double wp, const float th, const double thr_cur) {
   if (!has_prev) return w;
-  if (k == prev) return __ddiv_rn(w, P.p);                            // dense_rw.py:67 / :113
+  if (isprev) return __ddiv_rn(w, P.p);                               // dense_rw.py:67 / :113
   if (!EXTEND) {
-    if (!__ldg(nzprev + k)) w = __ddiv_rn(w, P.q);                    // :63-66
+    if (!nzp) w = P.q_pow2 ? __dmul_rn(w, (double)P.invq_f) : __ddiv_rn(w, P.q);   // :63-66 (exact for 2^k)
   } else {
-    double wp = __ldg(rprev + k);
-    double th = (double)__ldg(P.thr + k);
-    if (wp < th) {                                                    // :94
-      double t = __ddiv_rn(wp, th);                                   // :101
+    const double thd = (double)th;
+    if (wp < thd) {                                                   // :94
+      const double t = (wp == 0.0) ? 0.0 : __ddiv_rn(wp, thd);        // :101  (0 / thd == 0 exactly)
       double alpha = __dadd_rn(P.invq, __dmul_rn(__dsub_rn(1.0, P.invq), t));   // :106
       if (w < thr_cur) alpha = P.supp;                                // :109-111
       w = __dmul_rn(w, alpha);                                        // :112
     }
   }
   return w;
+}
+
+template <bool EXTEND, bool VEC>
+__device__ __forceinline__ void load_lane_tile(const WalkParams& P, const double* __restrict__ rcur,
+                                               const uint8_t* __restrict__ nzcur, const double* __restrict__ rprev,
+                                               const uint8_t* __restrict__ nzprev, const bool has_prev,
+                                               const uint32_t prev, const uint32_t k0, const uint32_t N,
+                                               const double thr_cur, LaneTile& out) {
+  uint32_t m4 = 0;
+  if (VEC) {
+    if (k0 < N) m4 = __ldg(reinterpret_cast<const uint32_t*>(nzcur + k0));
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (k0 + r < N && __ldg(nzcur + k0 + r)) m4 |= 0xFFu << (8 * r);
+  }
+  out.nzmask = 0;
+  out.w[0] = out.w[1] = out.w[2] = out.w[3] = 0.0;
+  if (m4 == 0) return;
+  double c[4], pv[4] = {0.0, 0.0, 0.0, 0.0};
+  float th[4] = {0.f, 0.f, 0.f, 0.f};
+  uint32_t mp4 = 0;
+  if (VEC) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(rcur + k0));
+    const double2 b = __ldg(reinterpret_cast<const double2*>(rcur + k0 + 2));
+    c[0] = a.x; c[1] = a.y; c[2] = b.x; c[3] = b.y;
+    if (has_prev) {
+      if (!EXTEND) {
+        mp4 = __ldg(reinterpret_cast<const uint32_t*>(nzprev + k0));
+      } else {
+        const double2 e = __ldg(reinterpret_cast<const double2*>(rprev + k0));
+        const double2 f = __ldg(reinterpret_cast<const double2*>(rprev + k0 + 2));
+        pv[0] = e.x; pv[1] = e.y; pv[2] = f.x; pv[3] = f.y;
+        const float4 t4 = __ldg(reinterpret_cast<const float4*>(P.thr + k0));
+        th[0] = t4.x; th[1] = t4.y; th[2] = t4.z; th[3] = t4.w;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      c[r] = 0.0;
+      if ((m4 >> (8 * r)) & 0xFFu) {
+        c[r] = __ldg(rcur + k0 + r);
+        if (has_prev) {
+          if (!EXTEND) { if (__ldg(nzprev + k0 + r)) mp4 |= 0xFFu << (8 * r); }
+          else { pv[r] = __ldg(rprev + k0 + r); th[r] = __ldg(P.thr + k0 + r); }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    if ((m4 >> (8 * r)) & 0xFFu) {
+      out.nzmask |= 1u << r;
+      out.w[r] = dense_weight<EXTEND>(P, c[r], has_prev, k0 + r == prev, ((mp4 >> (8 * r)) & 0xFFu) != 0, pv[r], th[r],
+                                      thr_cur);
+    }
+  }
 }
 
 __device__ __forceinline__ double warp_sum_f64(double v) {
@@ -60,7 +124,7 @@ __device__ __forceinline__ double warp_incl_scan_f64(double v, int lane) {
   return v;
 }
 
-template <bool EXTEND>
+template <bool EXTEND, bool VEC>
 __global__ void __launch_bounds__(DTHREADS) walk_dense_kernel(const WalkParams P, const uint32_t n_super) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* tile_sum = reinterpret_cast<double*>(smem_raw);             // [n_super] inclusive prefix after the scan
@@ -97,22 +161,11 @@ __global__ void __launch_bounds__(DTHREADS) walk_dense_kernel(const WalkParams P
       // ---- pass 1: one partial sum per 128-column super tile
       uint32_t cnt = 0, last = 0;
       for (uint32_t t = warp; t < n_super; t += DWARPS) {
-        const uint32_t base = t * SUPER + lane;
-        uint8_t nz[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          uint32_t k = base + 32 * r;
-          nz[r] = (k < N) ? __ldg(nzcur + k) : 0;
-        }
-        double acc = 0.0;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          uint32_t k = base + 32 * r;
-          if (nz[r]) {
-            acc = __dadd_rn(acc, dense_weight<EXTEND>(P, rcur, rprev, nzprev, has_prev, prev, k, thr_cur));
-            ++cnt; last = k;
-          }
-        }
+        const uint32_t k0 = t * SUPER + 4 * lane;
+        LaneTile lt;
+        load_lane_tile<EXTEND, VEC>(P, rcur, nzcur, rprev, nzprev, has_prev, prev, k0, N, thr_cur, lt);
+        double acc = __dadd_rn(__dadd_rn(lt.w[0], lt.w[1]), __dadd_rn(lt.w[2], lt.w[3]));
+        if (lt.nzmask) { cnt += __popc(lt.nzmask); last = k0 + 31 - __clz(lt.nzmask); }
         acc = warp_sum_f64(acc);
         if (lane == 0) tile_sum[t] = acc;
       }
@@ -133,22 +186,20 @@ __global__ void __launch_bounds__(DTHREADS) walk_dense_kernel(const WalkParams P
         const uint32_t b = lane * per, e = min(n_super, b + per);
         double loc = 0.0;
         for (uint32_t t = b; t < e; ++t) loc = __dadd_rn(loc, tile_sum[t]);
-        double incl = warp_incl_scan_f64(loc, lane);
+        const double incl = warp_incl_scan_f64(loc, lane);
         double run = __shfl_up_sync(B2W_FULL, incl, 1);   // exclusive prefix of this lane's segment
         if (lane == 0) run = 0.0;
         const double total = __shfl_sync(B2W_FULL, incl, 31);
         for (uint32_t t = b; t < e; ++t) { run = __dadd_rn(run, tile_sum[t]); tile_sum[t] = run; }
         __syncwarp();
-        // first super tile whose inclusive prefix possibly reaches u
+        // first super tile whose inclusive prefix possibly reaches u:  I_t (1 + EPS) >= u * total
+        const double uT = u * total;
         uint32_t found = 0xFFFFFFFFu;
         for (uint32_t t0 = 0; t0 < n_super && found == 0xFFFFFFFFu; t0 += 32) {
-          uint32_t t = t0 + lane;
+          const uint32_t t = t0 + lane;
           bool poss = false;
-          if (t < n_super) {
-            double A = __ddiv_rn(tile_sum[t], total);
-            poss = (A + EPS * A) >= u;
-          }
-          uint32_t bal = __ballot_sync(B2W_FULL, poss);
+          if (t < n_super) { const double I = tile_sum[t]; poss = fma(I, EPS, I) >= uT; }
+          const uint32_t bal = __ballot_sync(B2W_FULL, poss);
           if (bal) found = t0 + __ffs(bal) - 1;
         }
         uint32_t result;
@@ -157,28 +208,31 @@ __global__ void __launch_bounds__(DTHREADS) walk_dense_kernel(const WalkParams P
         } else if (found == 0xFFFFFFFFu) {
           result = 0xFFFFFFFEu;                                       // every prefix certainly < u: overflow
         } else {
-          // ---- pass 2: the located super tile, column order = (r, lane)
+          // ---- pass 2: the located super tile, column order = (lane, r)
           const double excl = found ? tile_sum[found - 1] : 0.0;
-          const uint32_t base = found * SUPER + lane;
-          double carry = excl;
-          result = 0xFFFFFFFFu;
-          bool done = false;
+          const uint32_t k0 = found * SUPER + 4 * lane;
+          LaneTile lt;
+          load_lane_tile<EXTEND, VEC>(P, rcur, nzcur, rprev, nzprev, has_prev, prev, k0, N, thr_cur, lt);
+          const double p0 = lt.w[0], p1 = __dadd_rn(p0, lt.w[1]), p2 = __dadd_rn(p1, lt.w[2]), p3 = __dadd_rn(p2, lt.w[3]);
+          const double sc = warp_incl_scan_f64(p3, lane);
+          const double base = __dadd_rn(excl, __dsub_rn(sc, p3));     // prefix before this lane's columns
+          const double A[4] = {__dadd_rn(base, p0), __dadd_rn(base, p1), __dadd_rn(base, p2), __dadd_rn(base, p3)};
+          uint32_t poss = 0, sure = 0;
 #pragma unroll
           for (int r = 0; r < 4; ++r) {
-            uint32_t k = base + 32 * r;
-            bool nzk = (k < N) && __ldg(nzcur + k);
-            double w = nzk ? dense_weight<EXTEND>(P, rcur, rprev, nzprev, has_prev, prev, k, thr_cur) : 0.0;
-            double sc = warp_incl_scan_f64(w, lane);
-            double A = __ddiv_rn(__dadd_rn(carry, sc), total);
-            double E = EPS * A;
-            uint32_t bp = __ballot_sync(B2W_FULL, nzk && (A + E >= u));
-            uint32_t bd = __ballot_sync(B2W_FULL, nzk && (A - E >= u));
-            if (!done && bp) {
-              int fp = __ffs(bp) - 1;
-              if (bd && (__ffs(bd) - 1) == fp) result = found * SUPER + 32 * r + fp;
-              done = true;   // first possible column seen: either proven or ambiguous
+            if ((lt.nzmask >> r) & 1u) {
+              const double E = A[r] * EPS;
+              if (A[r] + E >= uT) poss |= 1u << r;
+              if (A[r] - E >= uT) sure |= 1u << r;
             }
-            carry = __dadd_rn(carry, __shfl_sync(B2W_FULL, sc, 31));
+          }
+          const uint32_t bal = __ballot_sync(B2W_FULL, poss != 0);
+          result = 0xFFFFFFFFu;                                       // default: ambiguous (tile boundary) -> replay
+          if (bal) {
+            const int fl = __ffs(bal) - 1;
+            const uint32_t pm = __shfl_sync(B2W_FULL, poss, fl), sm = __shfl_sync(B2W_FULL, sure, fl);
+            const int r = __ffs(pm) - 1;
+            if ((sm >> r) & 1u) result = found * SUPER + 4 * fl + r;
           }
         }
         if (lane == 0) s_choice = result;
@@ -189,15 +243,21 @@ __global__ void __launch_bounds__(DTHREADS) walk_dense_kernel(const WalkParams P
         // ---- exact replay by one lane (dense_rw.py:69-70, pecanpy.py:608-612 verbatim order)
         if (threadIdx.x == 0) {
           double S = 0.0;
-          for (uint32_t k = 0; k < N; ++k)
-            if (__ldg(nzcur + k)) S = __dadd_rn(S, dense_weight<EXTEND>(P, rcur, rprev, nzprev, has_prev, prev, k, thr_cur));
+          for (uint32_t k0 = 0; k0 < N; k0 += 4) {
+            LaneTile lt;
+            load_lane_tile<EXTEND, false>(P, rcur, nzcur, rprev, nzprev, has_prev, prev, k0, N, thr_cur, lt);
+            for (int r = 0; r < 4; ++r) if ((lt.nzmask >> r) & 1u) S = __dadd_rn(S, lt.w[r]);
+          }
           double cdf = 0.0;
           uint32_t pick = 0xFFFFFFFEu;
-          for (uint32_t k = 0; k < N; ++k) {
-            if (!__ldg(nzcur + k)) continue;
-            double w = dense_weight<EXTEND>(P, rcur, rprev, nzprev, has_prev, prev, k, thr_cur);
-            cdf = __dadd_rn(cdf, __ddiv_rn(w, S));
-            if (!(cdf < u)) { pick = k; break; }
+          for (uint32_t k0 = 0; k0 < N && pick == 0xFFFFFFFEu; k0 += 4) {
+            LaneTile lt;
+            load_lane_tile<EXTEND, false>(P, rcur, nzcur, rprev, nzprev, has_prev, prev, k0, N, thr_cur, lt);
+            for (int r = 0; r < 4; ++r) {
+              if (!((lt.nzmask >> r) & 1u)) continue;
+              cdf = __dadd_rn(cdf, __ddiv_rn(lt.w[r], S));
+              if (!(cdf < u)) { pick = k0 + r; break; }
+            }
           }
           s_choice = pick;
           ++st_replays;
@@ -225,6 +285,18 @@ __global__ void __launch_bounds__(DTHREADS) walk_dense_kernel(const WalkParams P
   }
 }
 
+template <bool EXTEND, bool VEC>
+int launch_dense(const b2w_graph* g, const WalkParams& P, const uint32_t n_super, size_t smem, cudaStream_t s) {
+  int per_sm = 0;
+  B2W_CUDA(cudaFuncSetAttribute(walk_dense_kernel<EXTEND, VEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  B2W_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, walk_dense_kernel<EXTEND, VEC>, DTHREADS, smem));
+  if (per_sm < 1) per_sm = 1;
+  uint64_t grid = (uint64_t)per_sm * g->num_sms;
+  if (grid > P.n_rows) grid = P.n_rows ? P.n_rows : 1;
+  walk_dense_kernel<EXTEND, VEC><<<(unsigned)grid, DTHREADS, smem, s>>>(P, n_super);
+  return b2w_cuda_fail(cudaGetLastError(), "walk_dense_kernel launch");
+}
+
 }  // namespace
 
 int b2w_launch_dense(const b2w_graph* g, int extend, const WalkParams& P_in, cudaStream_t s) {
@@ -234,20 +306,10 @@ int b2w_launch_dense(const b2w_graph* g, int extend, const WalkParams& P_in, cud
   const uint32_t n_super = (g->n + SUPER - 1) / SUPER;
   size_t smem = (size_t)n_super * sizeof(double) + ((size_t)P.L + 2) * sizeof(uint32_t);
   if (smem > 200 * 1024) { b2w_set_error("dense walk: row too wide / walk too long for shared memory (%zu bytes)", smem); return B2W_ERR_UNSUPPORTED; }
-  int per_sm = 0;
-  if (extend) {
-    B2W_CUDA(cudaFuncSetAttribute(walk_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B2W_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, walk_dense_kernel<true>, DTHREADS, smem));
-  } else {
-    B2W_CUDA(cudaFuncSetAttribute(walk_dense_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B2W_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, walk_dense_kernel<false>, DTHREADS, smem));
-  }
-  if (per_sm < 1) per_sm = 1;
-  uint64_t grid = (uint64_t)per_sm * g->num_sms;
-  if (grid > P.n_rows) grid = P.n_rows ? P.n_rows : 1;
-  if (extend)
-    walk_dense_kernel<true><<<(unsigned)grid, DTHREADS, smem, s>>>(P, n_super);
-  else
-    walk_dense_kernel<false><<<(unsigned)grid, DTHREADS, smem, s>>>(P, n_super);
-  return b2w_cuda_fail(cudaGetLastError(), "walk_dense_kernel launch");
+  // vector loads need every row base 16/32-byte aligned: N % 4 == 0 and 16-byte aligned array bases
+  const bool vec = (g->n % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.dense) & 31) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(P.nonzero) & 3) == 0) &&
+                   (!extend || (reinterpret_cast<uintptr_t>(P.thr) & 15) == 0);
+  if (extend) return vec ? launch_dense<true, true>(g, P, n_super, smem, s) : launch_dense<true, false>(g, P, n_super, smem, s);
+  return vec ? launch_dense<false, true>(g, P, n_super, smem, s) : launch_dense<false, false>(g, P, n_super, smem, s);
 }
