@@ -75,7 +75,6 @@ __device__ __forceinline__ uint32_t otf_choice_warp(const WalkParams& P, const T
   const uint32_t lgp = 32 - __clz(pdeg);
   float thr_cur = 0.f;
   if (EXTEND && has_prev) thr_cur = __ldg(P.thr + cur);
-  float total = 0.f;
   for (uint32_t c = 0; c < nchunks; ++c) {
     const uint32_t k = (c << 5) + lane;
     const bool valid = k < d;
@@ -110,10 +109,7 @@ __device__ __forceinline__ uint32_t otf_choice_warp(const WalkParams& P, const T
         }
       }
     }
-    if (valid) wbuf[k] = w; else w = 0.f;
-    const float tot = warp_sum_f32(w);
-    if (lane == 0) ctot[c] = tot;
-    total = __fadd_rn(total, tot);
+    if (valid) wbuf[k] = w;
   }
   if (lane < 4) {                                                               // zero pad for float4 replay reads
     const uint32_t k = d + lane;
@@ -121,46 +117,48 @@ __device__ __forceinline__ uint32_t otf_choice_warp(const WalkParams& P, const T
   }
   __syncwarp();
 
+  // ---- lane-contiguous partial sums: lane l owns elements [l * mseg, (l + 1) * mseg) of the staged row
+  // (mseg odd: the strided shared-memory reads are bank-conflict free), one FADD per element and a
+  // single warp scan per step instead of a reduction per chunk.
+  const uint32_t mseg = nchunks | 1u;
+  const uint32_t seg_lo = min(d, (uint32_t)lane * mseg), seg_hi = min(d, seg_lo + mseg);
+  float seg = 0.f;
+  for (uint32_t i = seg_lo; i < seg_hi; ++i) seg = __fadd_rn(seg, wbuf[i]);
+  const float incl_l = warp_incl_scan_f32(seg, lane);
+  const float total = __shfl_sync(B2W_FULL, incl_l, 31);
+
   // ---- filter in the un-normalised domain: compare prefix sums with u * total
   uint32_t choice = d;                       // default: every bound below u -> the reference's choice == deg
   bool replay = (P.flags & B2W_FLAG_FORCE_EXACT_REPLAY) || !(total > 0.f) || !(total < 3.0e38f) || d > (1u << 20);
   if (!replay) {
     const double uT = u * (double)total;
     const double EC = 1.01 * 5.9604644775390625e-08;
-    const double ebase = (double)(d + 2 * nchunks + 40);
-    float carry = 0.f, excl_sel = 0.f;
-    uint32_t csel = B2W_NONE;
-    for (uint32_t c0 = 0; c0 < nchunks; c0 += 32) {
-      const uint32_t c = c0 + lane;
-      const bool valid = c < nchunks;
-      const float v = valid ? ctot[c] : 0.f;
-      const float incl = __fadd_rn(carry, warp_incl_scan_f32(v, lane));
-      const uint32_t kend = min(d, (c + 1) << 5) - 1;
-      const double A = (double)incl;
-      const uint32_t bal = __ballot_sync(B2W_FULL, valid && (fma(A, EC * (ebase + (double)kend), A) >= uT));
-      if (bal) {
-        const int src = __ffs(bal) - 1;
-        csel = c0 + src;
-        const float up = __shfl_up_sync(B2W_FULL, incl, 1);
-        excl_sel = __shfl_sync(B2W_FULL, lane == 0 ? carry : up, src);
-        break;
+    const double ebase = (double)(d + 2 * mseg + 48);
+    // lane level: first lane whose segment end possibly reaches u
+    const double Al = (double)incl_l;
+    const uint32_t bal = __ballot_sync(B2W_FULL, seg_hi > seg_lo && (fma(Al, EC * (ebase + (double)seg_hi), Al) >= uT));
+    if (bal) {
+      const int fl = __ffs(bal) - 1;
+      const uint32_t flo = __shfl_sync(B2W_FULL, seg_lo, fl), fhi = __shfl_sync(B2W_FULL, seg_hi, fl);
+      float carry = __shfl_sync(B2W_FULL, __fadd_rn(incl_l, -seg), fl);   // prefix before the segment (within bound)
+      bool decided = false;
+      for (uint32_t k0 = flo; k0 < fhi && !decided; k0 += 32) {
+        const uint32_t k = k0 + lane;
+        const bool valid = k < fhi;
+        const float w = valid ? wbuf[k] : 0.f;
+        const float sc = __fadd_rn(carry, warp_incl_scan_f32(w, lane));
+        const double A = (double)sc;
+        const double E = A * (EC * (ebase + (double)k));
+        const uint32_t bp = __ballot_sync(B2W_FULL, valid && (A + E >= uT));
+        if (bp) {
+          const int f = __ffs(bp) - 1;
+          const bool sure = __shfl_sync(B2W_FULL, (A - E >= uT) ? 1 : 0, f) != 0;
+          if (sure) choice = k0 + f; else replay = true;
+          decided = true;
+        }
+        carry = __shfl_sync(B2W_FULL, sc, 31);
       }
-      carry = __shfl_sync(B2W_FULL, incl, 31);
-    }
-    if (csel != B2W_NONE) {
-      const uint32_t k = (csel << 5) + lane;
-      const bool valid = k < d;
-      const float w = valid ? wbuf[k] : 0.f;
-      const double A = (double)__fadd_rn(excl_sel, warp_incl_scan_f32(w, lane));
-      const double E = A * (EC * (ebase + (double)k));
-      const uint32_t bp = __ballot_sync(B2W_FULL, valid && (A + E >= uT));
-      if (bp) {
-        const int f = __ffs(bp) - 1;
-        const bool sure = __shfl_sync(B2W_FULL, (A - E >= uT) ? 1 : 0, f) != 0;
-        if (sure) choice = (csel << 5) + f; else replay = true;
-      } else {
-        replay = true;                                                          // rounding at the chunk boundary
-      }
+      if (!decided) replay = true;                                              // rounding at the segment boundary
     }
   }
   if (replay) {
@@ -199,7 +197,7 @@ __device__ __forceinline__ uint32_t otf_choice_warp(const WalkParams& P, const T
 }
 
 template <bool EXTEND>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32) walk_sparse_warp_kernel(const WalkParams P) {
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) walk_sparse_warp_kernel(const WalkParams P) {
   __shared__ WarpBuf sbuf[WARPS_PER_CTA];
   const Tile<32> T;
   const int lane = threadIdx.x & 31;
