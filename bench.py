@@ -177,16 +177,17 @@ def algorithmic_bytes_precomp(torch, deg_t, walks_t, L: int) -> int:
 def cpu_port_rate(wl, g, start, L, budget_s: float, seed: int):
     """Time the C port of the reference on a bounded sample; returns (steps/s, cores, sample description)."""
     from oracle import oracle as orc
-    cores = orc.num_threads()
+    cores = host_threads()
 
     def run(rows):
         t0 = time.perf_counter()
         if g["kind"] == "dense":
             out = orc.walk_dense(g["data"], g["nonzero"], wl["p"], wl["q"], start[:rows], L, extend=wl["extend"],
-                                 thr=g.get("thr"), rng=orc.RNG_PHILOX, seed=seed)
+                                 thr=g.get("thr"), rng=orc.RNG_PHILOX, seed=seed, nthreads=cores)
         else:
             out = orc.walk_csr(wl["mode"], g["indptr"], g["indices"], g["data"], wl["p"], wl["q"], start[:rows], L,
-                               extend=wl["extend"], thr=g.get("thr"), alias=g.get("alias"), rng=orc.RNG_PHILOX, seed=seed)
+                               extend=wl["extend"], thr=g.get("thr"), alias=g.get("alias"), rng=orc.RNG_PHILOX, seed=seed,
+                               nthreads=cores)
         dt = time.perf_counter() - t0
         return int((out[:, -1].astype(np.int64) - 1).sum()), dt
 
@@ -245,10 +246,11 @@ def main():
             t0 = time.perf_counter()
             if g["kind"] == "dense":
                 out = orc.walk_dense(g["data"], g["nonzero"], wl["p"], wl["q"], start[:rows], L, extend=wl["extend"],
-                                     thr=g.get("thr"), rng=orc.RNG_PHILOX, seed=it)
+                                     thr=g.get("thr"), rng=orc.RNG_PHILOX, seed=it, nthreads=cores)
             else:
                 out = orc.walk_csr(wl["mode"], g["indptr"], g["indices"], g["data"], wl["p"], wl["q"], start[:rows], L,
-                                   extend=wl["extend"], thr=g.get("thr"), alias=g.get("alias"), rng=orc.RNG_PHILOX, seed=it)
+                                   extend=wl["extend"], thr=g.get("thr"), alias=g.get("alias"), rng=orc.RNG_PHILOX, seed=it,
+                                   nthreads=cores)
             dt = time.perf_counter() - t0
             if it >= W:
                 times.append(dt)
@@ -390,7 +392,7 @@ def main():
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(args.workload, {}).get("dram_bytes_per_launch")
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "kernel": kernel_name(wl), "kernel_ms": 1e3 * kernel_s,
+                    "traffic": traffic, "kernel": eng.kernel_name(wl["mode"], wl["p"], wl["q"], wl["extend"], args.flags), "kernel_ms": 1e3 * kernel_s,
                     "algorithmic_bytes_per_launch": alg, "bytes_per_step": alg / max(steps_mine, 1),
                     "formula": formula, "peak_source": peak_src}
 
@@ -444,9 +446,12 @@ def main():
     return 0
 
 
-def kernel_name(wl):
-    return {"SparseOTF": "walk_sparse_warp_kernel", "PreComp": "walk_thread_kernel<PRECOMP>",
-            "DenseOTF": "walk_dense_kernel"}[wl["mode"]]
+def host_threads() -> int:
+    """Host threads the CPU arm may use (torchrun exports OMP_NUM_THREADS=1; ask the OS instead)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:  # pragma: no cover
+        return max(1, os.cpu_count() or 1)
 
 
 def dtype_of(wl):

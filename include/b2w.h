@@ -67,6 +67,7 @@ typedef enum {
 #define B2W_FLAG_NO_FILTER_STATS 0x2u    /* do not update the fallback counters */
 #define B2W_FLAG_THREAD_PER_WALKER 0x4u  /* SparseOTF: use the lane-per-walker kernel */
 #define B2W_FLAG_NO_UNWEIGHTED_KERNEL 0x8u /* SparseOTF: always use the generic (weight-streaming) kernel */
+#define B2W_FLAG_NO_TMA 0x10u /* DenseOTF: per-lane vector loads instead of cp.async.bulk staging */
 #define B2W_FLAG_GROUP(n) (((uint32_t)(n) & 0xFFu) << 8) /* tuning: lanes per walker (8/16/32), 0 = auto */
 
 typedef struct b2w_graph b2w_graph; /* opaque */
@@ -156,6 +157,9 @@ int b2w_walk(const b2w_graph* g, int mode, double p, double q, int extend, const
              const uint32_t* d_start, uint64_t row0, uint64_t n_rows, uint32_t walk_length,
              uint64_t seed, int rng_mode, const double* d_feed, uint32_t* d_out, uint64_t ld_out,
              void* d_work, size_t work_bytes, b2w_walk_stats* d_stats, uint32_t flags, void* stream);
+
+/* Name of the kernel b2w_walk would launch for these arguments (static string; for logs/benchmarks). */
+const char* b2w_walk_kernel_name(const b2w_graph* g, int mode, double p, double q, int extend, uint32_t flags);
 
 /* Host-buffer convenience wrapper (the end-to-end call): copies h_start to the device in
  * batches, walks, and copies the rows back into h_out [n_rows, walk_length + 2]; H2D, kernel and

@@ -18,6 +18,7 @@ FLAG_FORCE_EXACT_REPLAY = 0x1
 FLAG_NO_FILTER_STATS = 0x2
 FLAG_THREAD_PER_WALKER = 0x4
 FLAG_NO_UNWEIGHTED_KERNEL = 0x8
+FLAG_NO_TMA = 0x10
 
 
 def FLAG_GROUP(n: int) -> int:
@@ -29,7 +30,7 @@ EXPORTS = [
     "b2w_version", "b2w_last_error", "b2w_device_count", "b2w_graph_csr_create", "b2w_graph_dense_create",
     "b2w_graph_info_get", "b2w_graph_destroy", "b2w_alias_build_work_bytes", "b2w_alias_build",
     "b2w_alias_build_first_order", "b2w_graph_set_alias", "b2w_walk_work_bytes", "b2w_walk", "b2w_walk_host",
-    "b2w_count_steps", "b2w_philox_selftest",
+    "b2w_count_steps", "b2w_philox_selftest", "b2w_walk_kernel_name",
 ]
 
 
@@ -77,6 +78,8 @@ def lib():
     L.b2w_walk_work_bytes.restype = sz
     L.b2w_walk.argtypes = [vp, i32, dbl, dbl, i32, vp, vp, u64, u64, u32, u64, i32, vp, vp, u64, vp, sz, vp, u32, vp]
     L.b2w_walk_host.argtypes = [vp, i32, dbl, dbl, i32, vp, vp, u64, u64, u32, u64, vp, u64, C.POINTER(WalkStats), u32]
+    L.b2w_walk_kernel_name.argtypes = [vp, i32, dbl, dbl, i32, u32]
+    L.b2w_walk_kernel_name.restype = C.c_char_p
     L.b2w_count_steps.argtypes = [vp, u64, u32, u64, vp, vp]
     L.b2w_philox_selftest.argtypes = [C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
     for name in EXPORTS:

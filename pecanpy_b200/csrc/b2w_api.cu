@@ -256,6 +256,21 @@ extern "C" int b2w_walk(const b2w_graph* g, int mode, double p, double q, int ex
   return b2w_launch_thread_walk(g, mode, ext, P, s);
 }
 
+extern "C" const char* b2w_walk_kernel_name(const b2w_graph* g, int mode, double p, double q, int extend, uint32_t flags) {
+  if (!g) return "";
+  switch (mode) {
+    case B2W_MODE_DENSE_OTF: return "walk_dense_kernel";
+    case B2W_MODE_PRECOMP: return "walk_thread_kernel<PRECOMP>";
+    case B2W_MODE_FIRST_ORDER_UNWEIGHTED: return "walk_thread_kernel<FIRST_ORDER_UNWEIGHTED>";
+    case B2W_MODE_PRECOMP_FIRST_ORDER: return "walk_thread_kernel<PRECOMP_FIRST_ORDER>";
+    case B2W_MODE_SPARSE_OTF:
+      if (flags & B2W_FLAG_THREAD_PER_WALKER) return "walk_thread_kernel<SPARSE_OTF>";
+      if (!extend && !(flags & B2W_FLAG_NO_UNWEIGHTED_KERNEL) && b2w_uw_eligible(g, p, q)) return "walk_uw_kernel";
+      return "walk_sparse_warp_kernel";
+  }
+  return "";
+}
+
 // ---------------------------------------------------------------- host-buffer wrapper
 extern "C" int b2w_walk_host(const b2w_graph* g, int mode, double p, double q, int extend, const float* d_thr,
                              const uint32_t* h_start, uint64_t row0, uint64_t n_rows, uint32_t L, uint64_t seed,

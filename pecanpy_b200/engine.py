@@ -212,6 +212,10 @@ class WalkEngine:
             self.last_stats = stats_t
         return out[:n_rows]
 
+    def kernel_name(self, mode, p: float, q: float, extend: bool = False, flags: int = 0) -> str:
+        mode = MODES[mode] if isinstance(mode, str) else int(mode)
+        return self.lib.b2w_walk_kernel_name(self.handle, mode, float(p), float(q), int(bool(extend)), int(flags)).decode()
+
     def stats(self) -> dict:
         if self.last_stats is None:
             return {}

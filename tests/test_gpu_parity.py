@@ -234,6 +234,28 @@ def test_power_law_hubs_weighted(mods):
         eng.close()
 
 
+@pytest.mark.parametrize("flags", [0, 0x10, 1], ids=["tma", "no-tma", "forced-replay"])
+@pytest.mark.parametrize("extend", [False, True], ids=["n2v", "n2v+"])
+@pytest.mark.parametrize("n", [256, 1040, 2064])
+def test_dense_tma_staging(mods, n, extend, flags):
+    """N % 16 == 0 selects the cp.async.bulk (TMA) staged pass 1: several tiles, a short tail tile, ring reuse
+    across steps; must equal the oracle and the LDG variant."""
+    from pecanpy_b200.synth import dense_weighted
+    orc = mods["orc"]
+    data, nz = dense_weighted(n, 0.3, seed=40 + n)
+    data[n - 3, :] = 0.0; data[:, n - 3] = 0.0                       # one isolated node -> dead ends
+    nz = data != 0
+    thr = orc.noise_thresholds_dense(data, nz, 0.25) if extend else None
+    start = orc.shuffled_start(n, 1, 9)[:300]
+    want = orc.walk_dense(data, nz, 0.5, 2.0, start, 12, extend=extend, thr=thr, rng=orc.RNG_PHILOX, seed=31)
+    eng = mods["WalkEngine"].from_dense(data, nz)
+    if extend:
+        eng.set_thresholds(thr)
+    got = to_np(eng.walk("DenseOTF", 0.5, 2.0, start, 12, seed=31, extend=extend, flags=flags))
+    assert np.array_equal(got, want), first_diff(got, want)
+    eng.close()
+
+
 def test_row_sharding_invariance_and_host_wrapper(mods):
     """Rows are keyed by the GLOBAL row index: any split of the start array gives the same matrix; the
     host-buffer entry point (b2w_walk_host, batched + pipelined) returns the same rows."""
