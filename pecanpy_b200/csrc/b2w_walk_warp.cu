@@ -34,6 +34,7 @@ struct __align__(16) WarpBuf {
   float w[CAP];
   float ctot[CAP / 32];
   uint32_t bm[CAP / 32];
+  uint32_t ht[B2W_HT_SLOTS];
 };
 
 struct WarpStats { uint32_t steps, replays, seqsums, overflow; };
@@ -59,7 +60,7 @@ __device__ __forceinline__ uint32_t otf_choice_warp(const WalkParams& P, const T
                                                     const uint32_t prev, const uint32_t ps, const uint32_t pdeg,
                                                     const double u, float* __restrict__ wbuf,
                                                     float* __restrict__ ctot, uint32_t* __restrict__ bm,
-                                                    WarpStats& st) {
+                                                    uint32_t* __restrict__ ht, WarpStats& st) {
   const int lane = T.lane;
   const uint32_t nchunks = (d + 31) >> 5;
   const uint32_t* const crow = P.indices + cs;
@@ -69,7 +70,7 @@ __device__ __forceinline__ uint32_t otf_choice_warp(const WalkParams& P, const T
 
   // ---- phase 1: membership (node2vec)
   uint32_t kp = B2W_NONE;
-  if (!EXTEND && has_prev) membership_bitmap<32>(T, crow, d, prow, pdeg, prev, bm, kp);
+  if (!EXTEND && has_prev) membership_bitmap<32>(T, crow, d, prow, pdeg, prev, bm, (P.flags & B2W_FLAG_NO_HASH) ? nullptr : ht, kp);
 
   // ---- phase 2: stream the weights, stage w, one partial sum per chunk
   const uint32_t lgp = 32 - __clz(pdeg);
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) walk_sparse_warp_kernel
       const bool small = deg + 4 <= CAP;
       const uint32_t choice = otf_choice_warp<EXTEND>(P, T, cur, cs, deg, j > 1, prev, ps, pdeg, u,
                                                       small ? sbuf[wib].w : gw, small ? sbuf[wib].ctot : gctot,
-                                                      small ? sbuf[wib].bm : gbm, st);
+                                                      small ? sbuf[wib].bm : gbm, sbuf[wib].ht, st);
       const uint32_t nxt = __ldg(P.indices + cs + choice);            // unchecked, as pecanpy.py:559
       if (lane == (j & 31)) myval = nxt;
       if ((j & 31) == 31) {                                           // entries [j-31, j] complete: flush
