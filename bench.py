@@ -191,19 +191,9 @@ def cpu_port_rate(wl, g, start, L, budget_s: float, seed: int):
         dt = time.perf_counter() - t0
         return int((out[:, -1].astype(np.int64) - 1).sum()), dt
 
-    # thread count: all hardware threads, or one per physical core if that is faster (SMT often hurts this
-    # latency-bound gather loop); a short probe decides
-    rows = min(start.size, 40000 if g["kind"] != "dense" else 512)
-    run(rows)                                               # warm-up (thread pool, page faults, clocks)
-    cores_all, half = cores, max(1, cores // 2)
-    best = {}
-    for nt in (cores_all, half, cores_all, half):
-        cores = nt
-        s_, dt_ = run(rows)
-        best[nt] = max(best.get(nt, 0.0), s_ / dt_)
-    cores = cores_all if best[cores_all] >= best[half] else half
-    # grow the sample until it runs for at least ~40% of the budget (a tiny probe is a poor predictor),
-    # capped by the budget and by the job size
+    # grow the sample until it runs for at least ~40% of the budget (thread start-up and cold caches make
+    # a tiny probe a poor predictor), capped by the budget and by the job size
+    rows = min(start.size, 4000 if g["kind"] != "dense" else 64)
     while True:
         s, dt = run(rows)
         if dt >= 0.4 * budget_s or rows >= start.size:
@@ -250,7 +240,6 @@ def main():
         start = synth.shuffled_start(g["n"], wl["num_walks"], 0)
         per_step_budget = max(2.0, 150.0 / max(K + W, 1))
         rate0, cores, _, rows = cpu_port_rate(wl, g, start, L, per_step_budget, seed=0)
-        cores_ref = cores
         times, steps = [], 0
         from oracle import oracle as orc
         for it in range(W + K):
