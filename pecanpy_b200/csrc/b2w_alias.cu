@@ -8,6 +8,8 @@
 // trip counts) and broadcast-read the same row of `cur`.
 // Reference: pecanpy.py:442-507 (preprocess_transition_probs), :336-361 (first order),
 //            rw/sparse_rw.py:51-130 (probabilities), pecanpy.py:617-665 (alias_setup).
+#include <cstdlib>
+
 #include "b2w_probs.cuh"
 
 namespace {
@@ -76,6 +78,91 @@ __global__ void __launch_bounds__(128) alias_build_kernel(const WalkParams P, co
   }
 }
 
+// Shared-memory variant (max degree <= ALIAS_SMEM_DEG): Vose's loop is a chain of dependent loads and stores
+// on q[], j[] and the two stacks; in global scratch every link costs an L2 round trip.  Here each warp
+// builds its 32 tables in shared memory, laid out [k][lane] with a 33-word pitch so that the lane-private,
+// data-dependent accesses of the construction AND the transposed (table-contiguous) write-out are both
+// bank-conflict free; the finished tables leave with coalesced 128-byte stores.
+constexpr int ALIAS_SMEM_DEG = 64;
+constexpr int ALIAS_WARPS = 4;
+constexpr int ALIAS_PITCH = 33;
+
+template <bool EXTEND, bool FIRST_ORDER>
+__global__ void __launch_bounds__(ALIAS_WARPS * 32) alias_build_smem_kernel(const WalkParams P,
+                                                                             const uint64_t* __restrict__ aip,
+                                                                             uint32_t* __restrict__ alias_j,
+                                                                             float* __restrict__ alias_q,
+                                                                             uint64_t n_tables) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int PER = ALIAS_SMEM_DEG * ALIAS_PITCH;
+  float* sq = reinterpret_cast<float*>(smem_raw) + (size_t)warp * 3 * PER;
+  uint32_t* sj = reinterpret_cast<uint32_t*>(sq + PER);
+  uint32_t* sk = sj + PER;
+  const uint64_t n_batches = (n_tables + 31) / 32;
+  for (uint64_t b = blockIdx.x * (uint64_t)ALIAS_WARPS + warp; b < n_batches; b += (uint64_t)gridDim.x * ALIAS_WARPS) {
+    const uint64_t t = b * 32 + lane;
+    uint32_t idx = 0, deg = 0, prev = 0;
+    uint64_t off = 0;
+    if (t < n_tables) {
+      if (FIRST_ORDER) {
+        idx = (uint32_t)t;
+        const uint32_t cs = P.indptr[idx];
+        deg = P.indptr[idx + 1] - cs;
+        off = cs;
+      } else {
+        uint32_t lo = 0, hi = P.n;
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi + 1) >> 1;
+          if ((uint64_t)P.indptr[mid] <= t) lo = mid; else hi = mid - 1;
+        }
+        idx = lo;
+        const uint32_t cs = P.indptr[idx];
+        deg = P.indptr[idx + 1] - cs;
+        prev = P.indices[t];
+        off = aip[idx] + (uint64_t)deg * (uint32_t)(t - cs);
+      }
+    }
+    // ---- probabilities (sequential f32 sum, rw/sparse_rw.py:89) into sq[k][lane]
+    if (deg) {
+      BiasStream<EXTEND> bs(P, idx, !FIRST_ORDER, prev);
+      float sum = 0.f;
+      for (uint32_t k = 0; k < deg; ++k) {
+        const float w = bs.weight(k);
+        sq[k * ALIAS_PITCH + lane] = w;
+        sum = __fadd_rn(sum, w);
+      }
+      // ---- alias_setup (pecanpy.py:632-665) entirely in shared memory
+      uint32_t sp = 0, lp = 0;
+      for (uint32_t kk = 0; kk < deg; ++kk) {
+        const float v = (float)__dmul_rn((double)deg, (double)__fdiv_rn(sq[kk * ALIAS_PITCH + lane], sum));
+        sq[kk * ALIAS_PITCH + lane] = v;
+        sj[kk * ALIAS_PITCH + lane] = 0;
+        if (v < 1.0f) sk[(sp++) * ALIAS_PITCH + lane] = kk; else sk[(deg - 1 - lp++) * ALIAS_PITCH + lane] = kk;
+      }
+      while (sp > 0 && lp > 0) {
+        const uint32_t small = sk[(--sp) * ALIAS_PITCH + lane];
+        const uint32_t large = sk[(deg - 1 - (--lp)) * ALIAS_PITCH + lane];
+        sj[small * ALIAS_PITCH + lane] = large;
+        const float v = (float)__dsub_rn((double)__fadd_rn(sq[large * ALIAS_PITCH + lane], sq[small * ALIAS_PITCH + lane]), 1.0);
+        sq[large * ALIAS_PITCH + lane] = v;
+        if (v < 1.0f) sk[(sp++) * ALIAS_PITCH + lane] = large; else sk[(deg - 1 - lp++) * ALIAS_PITCH + lane] = large;
+      }
+    }
+    __syncwarp();
+    // ---- coalesced write-out: table s of this batch is contiguous in global memory
+    for (int s2 = 0; s2 < 32; ++s2) {
+      const uint32_t dg = __shfl_sync(B2W_FULL, deg, s2);
+      const uint64_t of = __shfl_sync(B2W_FULL, off, s2);
+      for (uint32_t k = lane; k < dg; k += 32) {
+        alias_q[of + k] = sq[k * ALIAS_PITCH + s2];
+        alias_j[of + k] = sj[k * ALIAS_PITCH + s2];
+      }
+    }
+    __syncwarp();
+  }
+}
+
 uint64_t alias_threads(const b2w_graph* g) {
   // resident lanes, bounded so that the stack scratch stays below 256 MiB
   uint64_t lanes = (uint64_t)g->num_sms * 2048;
@@ -96,6 +183,7 @@ extern "C" size_t b2w_alias_build_work_bytes(const b2w_graph* g) {
 }
 
 static WalkParams alias_params(const b2w_graph* g, double p, double q, const float* d_thr);
+static bool g_alias_force_global = false;   // test hook (B2W_ALIAS_FORCE_GLOBAL=1): exercise the global-scratch builder
 
 static int alias_build_common(const b2w_graph* g, double p, double q, int extend, const float* d_thr,
                               const uint64_t* aip, uint32_t* aj, float* aq, void* d_work, size_t work_bytes,
@@ -110,14 +198,31 @@ static int alias_build_common(const b2w_graph* g, double p, double q, int extend
     return B2W_ERR_INVALID;
   }
   B2W_CUDA(cudaSetDevice(g->device));
+  { const char* e = getenv("B2W_ALIAS_FORCE_GLOBAL"); g_alias_force_global = e && e[0] == '1'; }
   WalkParams P = alias_params(g, p, q, d_thr);
   uint64_t lanes = alias_threads(g);
   uint64_t n_tables = first_order ? g->n : g->nnz;
   if (n_tables == 0) return B2W_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (g->max_degree <= (uint32_t)ALIAS_SMEM_DEG && !(g_alias_force_global)) {
+    const size_t smem = (size_t)ALIAS_WARPS * 3 * ALIAS_SMEM_DEG * ALIAS_PITCH * sizeof(float);
+    uint64_t nb = (n_tables + 32 * ALIAS_WARPS - 1) / (32 * ALIAS_WARPS);
+    uint64_t cap = (uint64_t)g->num_sms * 16;
+    unsigned blocks = (unsigned)(nb < cap ? nb : cap);
+#define B2W_ALIAS_SMEM(E, F)                                                                                        \
+    do {                                                                                                            \
+      B2W_CUDA(cudaFuncSetAttribute(alias_build_smem_kernel<E, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      alias_build_smem_kernel<E, F><<<blocks, ALIAS_WARPS * 32, smem, s>>>(P, aip, aj, aq, n_tables);             \
+    } while (0)
+    if (first_order) B2W_ALIAS_SMEM(false, true);
+    else if (extend) B2W_ALIAS_SMEM(true, false);
+    else B2W_ALIAS_SMEM(false, false);
+#undef B2W_ALIAS_SMEM
+    return b2w_cuda_fail(cudaGetLastError(), "alias_build_smem_kernel launch");
+  }
   uint64_t blocks = (n_tables + 127) / 128;
   if (blocks > lanes / 128) blocks = lanes / 128;
   uint32_t stride = g->max_degree ? g->max_degree : 1;
-  cudaStream_t s = (cudaStream_t)stream;
   if (first_order)
     alias_build_kernel<false, true><<<(unsigned)blocks, 128, 0, s>>>(P, aip, aj, aq, (uint32_t*)d_work, stride, n_tables);
   else if (extend)

@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <new>
 
 #include "b2w_common.cuh"
@@ -77,6 +78,56 @@ __global__ void dense_check_kernel(uint64_t total, const double* __restrict__ da
   if (bad_mask) atomicOr(&res->bad_order, 1u);
 }
 
+// Staging state of b2w_walk_host, cached in the handle so that repeated calls do not pay
+// cudaMalloc/cudaFree/stream creation again (a PreComp pass is ~2 ms of kernel time).
+struct b2w_host_pipe {
+  static constexpr int NS = 2;
+  std::mutex mu;
+  cudaStream_t st[NS] = {nullptr, nullptr};
+  uint32_t* d_start[NS] = {nullptr, nullptr};
+  uint32_t* d_out[NS] = {nullptr, nullptr};
+  void* d_work[NS] = {nullptr, nullptr};
+  b2w_walk_stats* d_stats = nullptr;
+  size_t start_cap = 0, out_cap = 0, work_cap = 0;
+  void release() {
+    for (int k = 0; k < NS; ++k) {
+      if (d_start[k]) cudaFree(d_start[k]);
+      if (d_out[k]) cudaFree(d_out[k]);
+      if (d_work[k]) cudaFree(d_work[k]);
+      if (st[k]) cudaStreamDestroy(st[k]);
+      d_start[k] = d_out[k] = nullptr; d_work[k] = nullptr; st[k] = nullptr;
+    }
+    if (d_stats) cudaFree(d_stats);
+    d_stats = nullptr;
+    start_cap = out_cap = work_cap = 0;
+  }
+  cudaError_t ensure(size_t start_bytes, size_t out_bytes, size_t work_bytes) {
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < NS && e == cudaSuccess; ++k)
+      if (!st[k]) e = cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking);
+    if (e == cudaSuccess && !d_stats) e = cudaMalloc(&d_stats, sizeof(b2w_walk_stats));
+    if (e == cudaSuccess && start_bytes > start_cap) {
+      for (int k = 0; k < NS && e == cudaSuccess; ++k) { if (d_start[k]) cudaFree(d_start[k]); d_start[k] = nullptr; e = cudaMalloc(&d_start[k], start_bytes); }
+      start_cap = e == cudaSuccess ? start_bytes : 0;
+    }
+    if (e == cudaSuccess && out_bytes > out_cap) {
+      for (int k = 0; k < NS && e == cudaSuccess; ++k) { if (d_out[k]) cudaFree(d_out[k]); d_out[k] = nullptr; e = cudaMalloc(&d_out[k], out_bytes); }
+      out_cap = e == cudaSuccess ? out_bytes : 0;
+    }
+    if (e == cudaSuccess && work_bytes > work_cap) {
+      for (int k = 0; k < NS && e == cudaSuccess; ++k) { if (d_work[k]) cudaFree(d_work[k]); d_work[k] = nullptr; e = cudaMalloc(&d_work[k], work_bytes); }
+      work_cap = e == cudaSuccess ? work_bytes : 0;
+    }
+    return e;
+  }
+};
+
+void b2w_host_pipe_destroy(b2w_host_pipe* p) {
+  if (!p) return;
+  p->release();
+  delete p;
+}
+
 static int new_handle(int device, b2w_graph** out, b2w_graph** gp) {
   if (!out) { b2w_set_error("graph create: null out"); return B2W_ERR_INVALID; }
   *out = nullptr;
@@ -89,6 +140,8 @@ static int new_handle(int device, b2w_graph** out, b2w_graph** gp) {
   cudaError_t e = cudaGetDeviceProperties(&prop, device);
   if (e != cudaSuccess) { delete g; return b2w_cuda_fail(e, "cudaGetDeviceProperties"); }
   g->num_sms = prop.multiProcessorCount;
+  g->pipe = new (std::nothrow) b2w_host_pipe();
+  if (!g->pipe) { delete g; b2w_set_error("graph create: out of host memory"); return B2W_ERR_NOMEM; }
   *gp = g;
   return B2W_OK;
 }
@@ -119,12 +172,12 @@ extern "C" int b2w_graph_csr_create(int device, uint32_t n, uint64_t nnz, const 
     Ctx* x = (Ctx*)c;
     csr_check_kernel<<<x->sms * 8, 256>>>(x->n, x->nnz, x->ip, x->ix, x->dt, d);
   }, &ctx);
-  if (rc) { delete g; return rc; }
+  if (rc) { b2w_host_pipe_destroy(g->pipe); delete g; return rc; }
   if (h.bad_indptr || h.bad_order || h.bad_index || h.bad_weight) {
     b2w_set_error("csr create: invalid graph (%s%s%s%s)", h.bad_indptr ? "indptr not monotone / inconsistent with nnz; " : "",
                   h.bad_order ? "a row is not sorted ascending and duplicate-free; " : "",
                   h.bad_index ? "column index out of range; " : "", h.bad_weight ? "negative, NaN or infinite weight" : "");
-    delete g;
+    b2w_host_pipe_destroy(g->pipe); delete g;
     return B2W_ERR_GRAPH;
   }
   g->max_degree = h.max_degree;
@@ -146,11 +199,11 @@ extern "C" int b2w_graph_dense_create(int device, uint32_t n, const double* d_da
     Ctx* x = (Ctx*)c;
     dense_check_kernel<<<x->sms * 16, 256>>>(x->total, x->d, x->z, d);
   }, &ctx);
-  if (rc) { delete g; return rc; }
+  if (rc) { b2w_host_pipe_destroy(g->pipe); delete g; return rc; }
   if (h.bad_weight || h.bad_order) {
     b2w_set_error("dense create: invalid graph (%s%s)", h.bad_weight ? "negative, NaN or infinite weight; " : "",
                   h.bad_order ? "nonzero mask != (data != 0)" : "");
-    delete g;
+    b2w_host_pipe_destroy(g->pipe); delete g;
     return B2W_ERR_GRAPH;
   }
   *out = g;
@@ -163,7 +216,12 @@ extern "C" int b2w_graph_info_get(const b2w_graph* g, b2w_graph_info* out) {
   return B2W_OK;
 }
 
-extern "C" void b2w_graph_destroy(b2w_graph* g) { delete g; }
+extern "C" void b2w_graph_destroy(b2w_graph* g) {
+  if (!g) return;
+  cudaSetDevice(g->device);
+  b2w_host_pipe_destroy(g->pipe);
+  delete g;
+}
 
 extern "C" int b2w_graph_set_alias(b2w_graph* g, const uint64_t* aip, const uint32_t* aj, const float* aq) {
   if (!g || !(g->flags & B2W_GRAPH_CSR)) { b2w_set_error("set_alias: CSR graph handle required"); return B2W_ERR_INVALID; }
@@ -279,54 +337,40 @@ extern "C" int b2w_walk_host(const b2w_graph* g, int mode, double p, double q, i
   if (n_rows == 0) return B2W_OK;
   if (!h_start || !h_out) { b2w_set_error("b2w_walk_host: null start/out"); return B2W_ERR_INVALID; }
   B2W_CUDA(cudaSetDevice(g->device));
-  if (batch_rows == 0) batch_rows = 1u << 20;
+  if (batch_rows == 0) batch_rows = 1u << 19;
   if (batch_rows > n_rows) batch_rows = n_rows;
   const uint64_t ld = (uint64_t)L + 2;
   const size_t wb = b2w_walk_work_bytes(g, mode);
-  constexpr int NS = 2;
-  cudaStream_t st[NS] = {nullptr, nullptr};
-  uint32_t* d_start[NS] = {nullptr, nullptr};
-  uint32_t* d_out[NS] = {nullptr, nullptr};
-  void* d_work[NS] = {nullptr, nullptr};
-  b2w_walk_stats* d_stats = nullptr;
+  b2w_host_pipe* pipe = g->pipe;
+  std::lock_guard<std::mutex> lock(pipe->mu);                          // one host-buffer call per handle at a time
+  constexpr int NS = b2w_host_pipe::NS;
   int rc = B2W_OK;
-  cudaError_t e = cudaSuccess;
-  for (int k = 0; k < NS && e == cudaSuccess; ++k) {
-    e = cudaStreamCreateWithFlags(&st[k], cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaMalloc(&d_start[k], batch_rows * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMalloc(&d_out[k], batch_rows * ld * sizeof(uint32_t));
-    if (e == cudaSuccess && wb) e = cudaMalloc(&d_work[k], wb);
-  }
-  if (e == cudaSuccess) e = cudaMalloc(&d_stats, sizeof(b2w_walk_stats));
-  if (e == cudaSuccess) e = cudaMemset(d_stats, 0, sizeof(b2w_walk_stats));
-  if (e != cudaSuccess) rc = b2w_cuda_fail(e, "b2w_walk_host setup");
+  cudaError_t e = pipe->ensure(batch_rows * sizeof(uint32_t), batch_rows * ld * sizeof(uint32_t), wb);
+  if (e == cudaSuccess) e = cudaMemsetAsync(pipe->d_stats, 0, sizeof(b2w_walk_stats), pipe->st[0]);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(pipe->st[0]);
+  if (e != cudaSuccess) { pipe->release(); return b2w_cuda_fail(e, "b2w_walk_host setup"); }
   uint64_t done = 0;
   for (int b = 0; rc == B2W_OK && done < n_rows; ++b) {
     const int k = b % NS;
     const uint64_t rows = (n_rows - done < batch_rows) ? (n_rows - done) : batch_rows;
     // the stream serialises reuse of this slot's buffers with its previous batch
-    e = cudaMemcpyAsync(d_start[k], h_start + done, rows * sizeof(uint32_t), cudaMemcpyHostToDevice, st[k]);
+    e = cudaMemcpyAsync(pipe->d_start[k], h_start + done, rows * sizeof(uint32_t), cudaMemcpyHostToDevice, pipe->st[k]);
     if (e != cudaSuccess) { rc = b2w_cuda_fail(e, "H2D start"); break; }
-    rc = b2w_walk(g, mode, p, q, extend, d_thr, d_start[k], row0 + done, rows, L, seed, B2W_RNG_PHILOX, nullptr,
-                  d_out[k], ld, d_work[k], wb, d_stats, flags, st[k]);
+    rc = b2w_walk(g, mode, p, q, extend, d_thr, pipe->d_start[k], row0 + done, rows, L, seed, B2W_RNG_PHILOX, nullptr,
+                  pipe->d_out[k], ld, pipe->d_work[k], wb, pipe->d_stats, flags, pipe->st[k]);
     if (rc) break;
-    e = cudaMemcpyAsync(h_out + done * ld, d_out[k], rows * ld * sizeof(uint32_t), cudaMemcpyDeviceToHost, st[k]);
+    e = cudaMemcpyAsync(h_out + done * ld, pipe->d_out[k], rows * ld * sizeof(uint32_t), cudaMemcpyDeviceToHost, pipe->st[k]);
     if (e != cudaSuccess) { rc = b2w_cuda_fail(e, "D2H walks"); break; }
     done += rows;
   }
-  for (int k = 0; k < NS; ++k)
-    if (st[k]) { e = cudaStreamSynchronize(st[k]); if (e != cudaSuccess && rc == B2W_OK) rc = b2w_cuda_fail(e, "b2w_walk_host sync"); }
+  for (int k = 0; k < NS; ++k) {
+    e = cudaStreamSynchronize(pipe->st[k]);
+    if (e != cudaSuccess && rc == B2W_OK) rc = b2w_cuda_fail(e, "b2w_walk_host sync");
+  }
   if (rc == B2W_OK && h_stats) {
-    e = cudaMemcpy(h_stats, d_stats, sizeof(b2w_walk_stats), cudaMemcpyDeviceToHost);
+    e = cudaMemcpy(h_stats, pipe->d_stats, sizeof(b2w_walk_stats), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) rc = b2w_cuda_fail(e, "stats D2H");
   }
-  for (int k = 0; k < NS; ++k) {
-    if (d_start[k]) cudaFree(d_start[k]);
-    if (d_out[k]) cudaFree(d_out[k]);
-    if (d_work[k]) cudaFree(d_work[k]);
-    if (st[k]) cudaStreamDestroy(st[k]);
-  }
-  if (d_stats) cudaFree(d_stats);
   return rc;
 }
 

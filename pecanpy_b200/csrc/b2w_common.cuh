@@ -7,6 +7,8 @@
 
 #define B2W_FULL 0xFFFFFFFFu
 
+struct b2w_host_pipe;
+
 struct b2w_graph {
   int device;
   uint32_t n;
@@ -25,8 +27,8 @@ struct b2w_graph {
   const uint64_t* alias_indptr;
   const uint32_t* alias_j;
   const float* alias_q;
-  // small device scratch owned by the handle
-  unsigned long long* d_counter;  // work-queue counters (one per concurrent launch slot)
+  // staging buffers / streams of b2w_walk_host (lazily allocated, guarded by their own mutex)
+  b2w_host_pipe* pipe;
 };
 
 // Parameters shared by every walk kernel (passed by value).

@@ -42,7 +42,10 @@ __device__ __forceinline__ double dense_weight(const WalkParams& P, double w, co
   } else {
     const double thd = (double)th;
     if (wp < thd) {                                                   // :94
-      const double t = (wp == 0.0) ? 0.0 : __ddiv_rn(wp, thd);        // :101  (0 / thd == 0 exactly)
+      // :101.  0 / thd == +0 exactly (70 % of the columns: non-neighbours of prev); a zero numerator would
+      // send the whole warp through the IEEE division's slow-path subroutine, so those lanes divide thd / thd
+      double t = __ddiv_rn(wp == 0.0 ? thd : wp, thd);
+      if (wp == 0.0) t = 0.0;
       double alpha = __dadd_rn(P.invq, __dmul_rn(__dsub_rn(1.0, P.invq), t));   // :106
       if (w < thr_cur) alpha = P.supp;                                // :109-111
       w = __dmul_rn(w, alpha);                                        // :112

@@ -157,6 +157,27 @@ def test_precomp_tables_and_walks(mods, name):
     eng.close()
 
 
+@pytest.mark.parametrize("extend", [False, True], ids=["n2v", "n2v+"])
+def test_precomp_tables_hub_graph(mods, extend):
+    """max degree > 64: the global-scratch table builder (the fixtures above use the shared-memory one)."""
+    c = load("hub400_sparseotf_ext")
+    orc = mods["orc"]
+    assert int((c["indptr"][1:] - c["indptr"][:-1]).max()) > 64
+    eng = mods["WalkEngine"].from_csr(c["indptr"], c["indices"], c["data"])
+    if extend:
+        eng.set_thresholds(c["thr"])
+    aip, aj, aq = eng.build_alias(c["indptr"], 0.7, 0.3, extend=extend)
+    o_aip, o_j, o_q = orc.alias_build(c["indptr"], c["indices"], c["data"], 0.7, 0.3, extend, c["thr"] if extend else None)
+    assert np.array_equal(aip, o_aip)
+    assert np.array_equal(to_np(aj), o_j)
+    assert np.array_equal(to_np(aq), o_q.view(np.uint32))
+    want = orc.walk_csr("PreComp", c["indptr"], c["indices"], c["data"], 0.7, 0.3, c["start"], 20,
+                        alias=(o_aip, o_j, o_q), rng=orc.RNG_PHILOX, seed=123)
+    got = to_np(eng.walk("PreComp", 0.7, 0.3, c["start"], 20, seed=123))
+    assert np.array_equal(got, want), first_diff(got, want)
+    eng.close()
+
+
 @pytest.mark.parametrize("name", ["testwalk_FirstOrderUnweighted", "karate_firstorder"])
 def test_first_order_unweighted(mods, name):
     c = load(name)
@@ -270,6 +291,12 @@ def test_row_sharding_invariance_and_host_wrapper(mods):
     assert np.array_equal(np.vstack([a, b]), full)
     host = eng.walk_host("SparseOTF", 4, 0.25, start, 30, seed=3, batch_rows=100)
     assert np.array_equal(host, full)
+    # the staging buffers are cached in the handle: repeated calls with other shapes must still be right
+    host2 = eng.walk_host("SparseOTF", 4, 0.25, start, 30, seed=3, batch_rows=333)
+    assert np.array_equal(host2, full)
+    long = to_np(eng.walk("SparseOTF", 4, 0.25, start[:50], 70, seed=4))
+    assert np.array_equal(eng.walk_host("SparseOTF", 4, 0.25, start[:50], 70, seed=4), long)
+    assert eng.last_host_stats["steps"] == int((long[:, -1].astype(np.int64) - 1).sum())
     eng.close()
 
 
