@@ -191,9 +191,19 @@ def cpu_port_rate(wl, g, start, L, budget_s: float, seed: int):
         dt = time.perf_counter() - t0
         return int((out[:, -1].astype(np.int64) - 1).sum()), dt
 
-    # grow the sample until it runs for at least ~40% of the budget (thread start-up and cold caches make
-    # a tiny probe a poor predictor), capped by the budget and by the job size
-    rows = min(start.size, 4000 if g["kind"] != "dense" else 64)
+    # thread count: all hardware threads, or one per physical core if that is faster (SMT often hurts this
+    # latency-bound gather loop); a short probe decides
+    rows = min(start.size, 40000 if g["kind"] != "dense" else 512)
+    run(rows)                                               # warm-up (thread pool, page faults, clocks)
+    cores_all, half = cores, max(1, cores // 2)
+    best = {}
+    for nt in (cores_all, half, cores_all, half):
+        cores = nt
+        s_, dt_ = run(rows)
+        best[nt] = max(best.get(nt, 0.0), s_ / dt_)
+    cores = cores_all if best[cores_all] >= best[half] else half
+    # grow the sample until it runs for at least ~40% of the budget (a tiny probe is a poor predictor),
+    # capped by the budget and by the job size
     while True:
         s, dt = run(rows)
         if dt >= 0.4 * budget_s or rows >= start.size:

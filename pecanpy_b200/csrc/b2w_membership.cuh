@@ -68,71 +68,18 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__
 //            O(deg(prev) log deg(cur)) words of row(cur); needs the bitmap zeroed first)
 // `prev` itself never counts as common (rw/sparse_rw.py:84); its position is returned in `kp`
 // (B2W_NONE when prev is not a neighbour of cur: directed graphs, or after a choice == deg overflow).
-// When both rows have at most 64 entries and the caller provides a 128-slot shared-memory table `ht`, an
-// exact open-addressing hash set of N(prev) replaces the binary searches (O(d + pdeg), no dependent global loads).
 // Returns the number of common neighbours.  Ends with a group sync: the bitmap is visible to all lanes.
-constexpr int B2W_HT_SLOTS = 128;          // open-addressing table per group (shared memory)
-constexpr uint32_t B2W_HT_MAXKEYS = 64;    // load factor <= 0.5
-
-__device__ __forceinline__ uint32_t ht_hash(uint32_t y) { return (y * 2654435761u) >> (32 - 7); }
-
 template <int G>
 __device__ __forceinline__ uint32_t membership_bitmap(const Tile<G>& T, const uint32_t* __restrict__ crow,
                                                       const uint32_t d, const uint32_t* __restrict__ prow,
                                                       const uint32_t pdeg, const uint32_t prev,
-                                                      uint32_t* __restrict__ bm, uint32_t* __restrict__ ht,
-                                                      uint32_t& kp) {
+                                                      uint32_t* __restrict__ bm, uint32_t& kp) {
   const uint32_t nwords = (d + 31) >> 5;
-  uint32_t m = 0;
-  kp = B2W_NONE;
-  if (ht != nullptr && d <= B2W_HT_MAXKEYS && pdeg <= B2W_HT_MAXKEYS) {
-    // ---- both rows small (the common case): exact hash set of N(prev) in shared memory, one probe
-    // sequence per neighbour of cur -- O(d + pdeg) work and no dependent global loads.
-    for (uint32_t i = T.tl; i < (uint32_t)B2W_HT_SLOTS; i += G) ht[i] = B2W_NONE;
-    T.sync();
-    for (uint32_t c0 = 0; c0 < pdeg; c0 += G) {
-      const uint32_t ii = c0 + T.tl;
-      if (ii < pdeg) {
-        const uint32_t y = __ldg(prow + ii);
-        uint32_t slot = ht_hash(y);
-        for (;;) {
-          const uint32_t old = atomicCAS(&ht[slot], B2W_NONE, y);
-          if (old == B2W_NONE || old == y) break;
-          slot = (slot + 1) & (B2W_HT_SLOTS - 1);
-        }
-      }
-    }
-    T.sync();
-    for (uint32_t c0 = 0; c0 < d; c0 += G) {
-      const uint32_t k = c0 + T.tl;
-      const bool valid = k < d;
-      bool found = false;
-      uint32_t x = B2W_NONE;
-      if (valid) {
-        x = __ldg(crow + k);
-        uint32_t slot = ht_hash(x);
-        for (;;) {
-          const uint32_t v = ht[slot];
-          if (v == x) { found = true; break; }
-          if (v == B2W_NONE) break;
-          slot = (slot + 1) & (B2W_HT_SLOTS - 1);
-        }
-      }
-      const bool isprev = valid && (x == prev);
-      const uint32_t bprev = T.ballot(isprev);
-      if (bprev) kp = c0 + __ffs(bprev) - 1;
-      const uint32_t bal = T.ballot(found && !isprev);
-      if (T.tl == 0) {
-        if (G == 32 || (c0 & 31) == 0) bm[c0 >> 5] = bal; else bm[c0 >> 5] |= bal << (c0 & 31);
-      }
-      m += __popc(bal);
-    }
-    T.sync();
-    return m;
-  }
   const uint32_t lgp = 32 - __clz(pdeg), lgd = 32 - __clz(d);
   const uint32_t fwd_cost = ((d + G - 1) / G) * (lgp + 2);
   const uint32_t rev_cost = ((pdeg + G) / G) * (lgd + 2) + (nwords + G - 1) / G;
+  uint32_t m = 0;
+  kp = B2W_NONE;
   if (fwd_cost <= rev_cost) {
     for (uint32_t c0 = 0; c0 < d; c0 += G) {
       const uint32_t k = c0 + T.tl;

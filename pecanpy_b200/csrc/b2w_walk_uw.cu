@@ -128,7 +128,6 @@ template <int G, int MINB>
 __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_kernel(const WalkParams P, const UwConsts C) {
   constexpr int GROUPS = UW_THREADS / G;
   __shared__ uint32_t s_bm[GROUPS][UW_BW];
-  __shared__ uint32_t s_ht[GROUPS][B2W_HT_SLOTS];
   const Tile<G> T;
   const int gib = threadIdx.x / G;                                   // group in block
   const uint32_t ggid = blockIdx.x * GROUPS + gib;                    // global group id
@@ -167,7 +166,7 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_kernel(const WalkPar
 
       // ---------------- phase 1: membership bitmap over the positions of row(cur)
       uint32_t m = 0, kp = NONE;
-      if (has_prev) m = membership_bitmap<G>(T, crow, d, prow, pdeg, prev, bm, (P.flags & B2W_FLAG_NO_HASH) ? nullptr : s_ht[gib], kp);
+      if (has_prev) m = membership_bitmap<G>(T, crow, d, prow, pdeg, prev, bm, kp);
 
       // ---------------- phase 2: exact normaliser, three-valued probabilities
       const float w_o = has_prev ? C.w_out : 1.0f;                    // first step: every weight is 1

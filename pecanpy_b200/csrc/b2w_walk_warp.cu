@@ -34,7 +34,6 @@ struct __align__(16) WarpBuf {
   float w[CAP];
   float ctot[CAP / 32];
   uint32_t bm[CAP / 32];
-  uint32_t ht[B2W_HT_SLOTS];
 };
 
 struct WarpStats { uint32_t steps, replays, seqsums, overflow; };
@@ -60,7 +59,7 @@ __device__ __forceinline__ uint32_t otf_choice_warp(const WalkParams& P, const T
                                                     const uint32_t prev, const uint32_t ps, const uint32_t pdeg,
                                                     const double u, float* __restrict__ wbuf,
                                                     float* __restrict__ ctot, uint32_t* __restrict__ bm,
-                                                    uint32_t* __restrict__ ht, WarpStats& st) {
+                                                    WarpStats& st) {
   const int lane = T.lane;
   const uint32_t nchunks = (d + 31) >> 5;
   const uint32_t* const crow = P.indices + cs;
@@ -70,7 +69,7 @@ __device__ __forceinline__ uint32_t otf_choice_warp(const WalkParams& P, const T
 
   // ---- phase 1: membership (node2vec)
   uint32_t kp = B2W_NONE;
-  if (!EXTEND && has_prev) membership_bitmap<32>(T, crow, d, prow, pdeg, prev, bm, (P.flags & B2W_FLAG_NO_HASH) ? nullptr : ht, kp);
+  if (!EXTEND && has_prev) membership_bitmap<32>(T, crow, d, prow, pdeg, prev, bm, kp);
 
   // ---- phase 2: stream the weights, stage w, one partial sum per chunk
   const uint32_t lgp = 32 - __clz(pdeg);
@@ -84,8 +83,11 @@ __device__ __forceinline__ uint32_t otf_choice_warp(const WalkParams& P, const T
     if (has_prev) {
       if (!EXTEND) {
         const uint32_t bits = bm[c];
-        if (k == kp) w = div_by(wt, P.p, P.invp_f, P.p_pow2);                  // return bias (sparse_rw.py:87)
-        else if (!((bits >> lane) & 1u)) w = div_by(wt, P.q, P.invq_f, P.q_pow2);   // out bias (:86)
+        // (invalid lanes keep w = 0: a zero numerator would take the f64 division's slow-path subroutine)
+        if (valid) {
+          if (k == kp) w = div_by(wt, P.p, P.invp_f, P.p_pow2);                // return bias (sparse_rw.py:87)
+          else if (!((bits >> lane) & 1u)) w = div_by(wt, P.q, P.invq_f, P.q_pow2);   // out bias (:86)
+        }
       } else {
         const uint32_t x = valid ? __ldg(crow + k) : B2W_NONE;
         const uint32_t pos = lower_bound_u32(prow, pdeg, x, lgp);
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) walk_sparse_warp_kernel
       const bool small = deg + 4 <= CAP;
       const uint32_t choice = otf_choice_warp<EXTEND>(P, T, cur, cs, deg, j > 1, prev, ps, pdeg, u,
                                                       small ? sbuf[wib].w : gw, small ? sbuf[wib].ctot : gctot,
-                                                      small ? sbuf[wib].bm : gbm, sbuf[wib].ht, st);
+                                                      small ? sbuf[wib].bm : gbm, st);
       const uint32_t nxt = __ldg(P.indices + cs + choice);            // unchecked, as pecanpy.py:559
       if (lane == (j & 31)) myval = nxt;
       if ((j & 31) == 31) {                                           // entries [j-31, j] complete: flush
