@@ -44,7 +44,10 @@ __device__ __forceinline__ double dense_weight(const WalkParams& P, double w, co
     if (wp < thd) {                                                   // :94
       // :101.  0 / thd == +0 exactly (70 % of the columns: non-neighbours of prev); a zero numerator would
       // send the whole warp through the IEEE division's slow-path subroutine, so those lanes divide thd / thd
-      double t = __ddiv_rn(wp == 0.0 ? thd : wp, thd);
+      // (the asm makes the substituted numerator opaque, otherwise the optimiser folds it back to wp / thd)
+      double num = (wp == 0.0) ? thd : wp;
+      asm volatile("" : "+d"(num));
+      double t = __ddiv_rn(num, thd);
       if (wp == 0.0) t = 0.0;
       double alpha = __dadd_rn(P.invq, __dmul_rn(__dsub_rn(1.0, P.invq), t));   // :106
       if (w < thr_cur) alpha = P.supp;                                // :109-111
