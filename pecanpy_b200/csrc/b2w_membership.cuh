@@ -80,7 +80,9 @@ __device__ __forceinline__ uint32_t membership_bitmap(const Tile<G>& T, const ui
   const uint32_t rev_cost = ((pdeg + G) / G) * (lgd + 2) + (nwords + G - 1) / G;
   uint32_t m = 0;
   kp = B2W_NONE;
-  if (fwd_cost <= rev_cost) {
+  // rows of cur that fit a few chunks always take the forward direction: the choice then does not depend on
+  // deg(prev), so the groups of one warp stay on the same path (no divergence between walkers)
+  if (d <= 2 * 32 || fwd_cost <= rev_cost) {
     for (uint32_t c0 = 0; c0 < d; c0 += G) {
       const uint32_t k = c0 + T.tl;
       const bool valid = k < d;
