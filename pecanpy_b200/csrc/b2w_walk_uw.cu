@@ -124,6 +124,97 @@ __device__ __noinline__ uint32_t replay_exact(const uint32_t* __restrict__ bm, c
   return d;                                                           // cdf[-1] < u: the reference's overflow
 }
 
+// One SparseOTF step of one walker by a group of G lanes: membership bitmap, exact normaliser, filter,
+// exact replay.  All arguments are group-uniform; `bm` is a group-private bitmap of >= ceil(d / 32) words.
+// Returns the reference's `choice` (== d for its cdf[-1] < u overflow).  Ends with a group sync.
+template <int G>
+__device__ __forceinline__ uint32_t uw_step(const Tile<G>& T, const WalkParams& P, const UwConsts& C,
+                                            const uint32_t* __restrict__ crow, const uint32_t d,
+                                            const uint32_t* __restrict__ prow, const uint32_t pdeg, const uint32_t prev,
+                                            const bool has_prev, const double u, uint32_t* __restrict__ bm,
+                                            uint32_t& st_replays, uint32_t& st_overflow) {
+  const double EC = 1.01 * 5.9604644775390625e-08;                    // 1.01 * 2^-24
+  const uint32_t nwords = (d + 31) >> 5;
+  // ---------------- phase 1: membership bitmap over the positions of row(cur)
+  uint32_t m = 0, kp = NONE;
+  if (has_prev) m = membership_bitmap<G>(T, crow, d, prow, pdeg, prev, bm, kp);
+
+  // ---------------- phase 2: exact normaliser, three-valued probabilities
+  const float w_o = has_prev ? C.w_out : 1.0f;                    // first step: every weight is 1
+  const uint32_t h = (kp != NONE) ? 1u : 0u;
+  const uint32_t n_o = d - m - h;
+  const double Tw = fma((double)n_o, (double)w_o, fma((double)h, (double)C.w_ret, (double)m));   // exact
+  const float S = (float)Tw;                                      // exact (host-verified precondition)
+  const float fa = __fdiv_rn(1.0f, S);
+  const float fo = !has_prev ? fa : (C.out_pow2 ? __fmul_rn(fa, w_o) : __fdiv_rn(w_o, S));
+  const float fp = C.ret_pow2 ? __fmul_rn(fa, C.w_ret) : __fdiv_rn(C.w_ret, S);
+  const double po = (double)fo, dpa = (double)fa - po, dpp = (double)fp - po;
+
+  uint32_t choice = d;                                            // default: cdf[-1] < u (overflow)
+  bool replay = (P.flags & B2W_FLAG_FORCE_EXACT_REPLAY) != 0;
+  if (!replay) {
+    // T_k = (k+1) po + n_in(k) (pa - po) + [kp <= k] (pp - po), all in f64 (filter arithmetic only)
+    uint32_t wsel = 0, bits_sel = 0, nc_before = 0;
+    if (nwords > 1) {
+      // word level: first word whose last position possibly reaches u
+      uint32_t carry = 0;
+      wsel = NONE;
+      for (uint32_t w0 = 0; w0 < nwords; w0 += G) {
+        const uint32_t w = w0 + T.tl;
+        const bool valid = w < nwords;
+        const uint32_t bits = (valid && has_prev) ? bm[w] : 0u;
+        const uint32_t cnt = __popc(bits);
+        const uint32_t incl = T.incl_scan(cnt) + carry;
+        const uint32_t kend = min(d, (w + 1) << 5) - 1;
+        double Tk = fma((double)(kend + 1), po, (double)incl * dpa);
+        if (kp <= kend) Tk += dpp;                                // NONE compares false
+        const double hi_b = fma(Tk, EC * (double)(kend + 2), Tk);
+        const uint32_t bal = T.ballot(valid && (hi_b >= u));
+        if (bal) {
+          const int src = __ffs(bal) - 1;
+          wsel = w0 + src;
+          bits_sel = T.shfl(bits, src);
+          nc_before = T.shfl(incl - cnt, src);
+          break;
+        }
+        carry = T.shfl(incl, G - 1);
+      }
+    } else if (has_prev) {
+      bits_sel = bm[0];
+    }
+    if (wsel != NONE) {
+      // position level inside the selected word
+      bool decided = false;
+      const uint32_t nb = min(32u, d - (wsel << 5));
+      for (uint32_t r0 = 0; r0 < nb && !decided; r0 += G) {
+        const uint32_t b = r0 + T.tl;
+        const uint32_t k = (wsel << 5) + b;
+        const bool valid = b < nb;
+        const uint32_t nc = nc_before + __popc(bits_sel & (0xFFFFFFFFu >> (31 - (b & 31))));
+        double Tk = fma((double)(k + 1), po, (double)nc * dpa);
+        if (kp <= k) Tk += dpp;
+        const double Ek = Tk * (EC * (double)(k + 2));
+        const uint32_t bp = T.ballot(valid && (Tk + Ek >= u));
+        if (bp) {
+          const int f = __ffs(bp) - 1;
+          const bool sure = T.shfl((Tk - Ek >= u) ? 1 : 0, f) != 0;
+          if (sure) choice = (wsel << 5) + r0 + f; else replay = true;
+          decided = true;
+        }
+      }
+      if (!decided) replay = true;                               // rounding at the word boundary
+    }
+  }
+  if (replay) {
+    choice = replay_exact<G>(bm, has_prev, nwords, d, kp, fa, fo, fp, u);
+    ++st_replays;
+  }
+  if (choice == d) ++st_overflow;
+  T.sync();                                                       // bitmap is rewritten by the next step
+
+  return choice;
+}
+
 template <int G, int MINB>
 __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_kernel(const WalkParams P, const UwConsts C) {
   constexpr int GROUPS = UW_THREADS / G;
@@ -133,7 +224,6 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_kernel(const WalkPar
   const uint32_t ggid = blockIdx.x * GROUPS + gib;                    // global group id
   uint32_t* const gbm = C.gbm + (size_t)ggid * C.gbm_stride;
   const uint32_t L = P.L;
-  const double EC = 1.01 * 5.9604644775390625e-08;                    // 1.01 * 2^-24
   uint32_t st_steps = 0, st_replays = 0, st_overflow = 0;
 
   for (;;) {
@@ -164,82 +254,7 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_kernel(const WalkPar
       uint32_t* const bm = (nwords <= UW_BW) ? s_bm[gib] : gbm;
       const uint32_t* const crow = P.indices + cs;
 
-      // ---------------- phase 1: membership bitmap over the positions of row(cur)
-      uint32_t m = 0, kp = NONE;
-      if (has_prev) m = membership_bitmap<G>(T, crow, d, prow, pdeg, prev, bm, kp);
-
-      // ---------------- phase 2: exact normaliser, three-valued probabilities
-      const float w_o = has_prev ? C.w_out : 1.0f;                    // first step: every weight is 1
-      const uint32_t h = (kp != NONE) ? 1u : 0u;
-      const uint32_t n_o = d - m - h;
-      const double Tw = fma((double)n_o, (double)w_o, fma((double)h, (double)C.w_ret, (double)m));   // exact
-      const float S = (float)Tw;                                      // exact (host-verified precondition)
-      const float fa = __fdiv_rn(1.0f, S);
-      const float fo = !has_prev ? fa : (C.out_pow2 ? __fmul_rn(fa, w_o) : __fdiv_rn(w_o, S));
-      const float fp = C.ret_pow2 ? __fmul_rn(fa, C.w_ret) : __fdiv_rn(C.w_ret, S);
-      const double po = (double)fo, dpa = (double)fa - po, dpp = (double)fp - po;
-
-      uint32_t choice = d;                                            // default: cdf[-1] < u (overflow)
-      bool replay = (P.flags & B2W_FLAG_FORCE_EXACT_REPLAY) != 0;
-      if (!replay) {
-        // T_k = (k+1) po + n_in(k) (pa - po) + [kp <= k] (pp - po), all in f64 (filter arithmetic only)
-        uint32_t wsel = 0, bits_sel = 0, nc_before = 0;
-        if (nwords > 1) {
-          // word level: first word whose last position possibly reaches u
-          uint32_t carry = 0;
-          wsel = NONE;
-          for (uint32_t w0 = 0; w0 < nwords; w0 += G) {
-            const uint32_t w = w0 + T.tl;
-            const bool valid = w < nwords;
-            const uint32_t bits = (valid && has_prev) ? bm[w] : 0u;
-            const uint32_t cnt = __popc(bits);
-            const uint32_t incl = T.incl_scan(cnt) + carry;
-            const uint32_t kend = min(d, (w + 1) << 5) - 1;
-            double Tk = fma((double)(kend + 1), po, (double)incl * dpa);
-            if (kp <= kend) Tk += dpp;                                // NONE compares false
-            const double hi_b = fma(Tk, EC * (double)(kend + 2), Tk);
-            const uint32_t bal = T.ballot(valid && (hi_b >= u));
-            if (bal) {
-              const int src = __ffs(bal) - 1;
-              wsel = w0 + src;
-              bits_sel = T.shfl(bits, src);
-              nc_before = T.shfl(incl - cnt, src);
-              break;
-            }
-            carry = T.shfl(incl, G - 1);
-          }
-        } else if (has_prev) {
-          bits_sel = bm[0];
-        }
-        if (wsel != NONE) {
-          // position level inside the selected word
-          bool decided = false;
-          const uint32_t nb = min(32u, d - (wsel << 5));
-          for (uint32_t r0 = 0; r0 < nb && !decided; r0 += G) {
-            const uint32_t b = r0 + T.tl;
-            const uint32_t k = (wsel << 5) + b;
-            const bool valid = b < nb;
-            const uint32_t nc = nc_before + __popc(bits_sel & (0xFFFFFFFFu >> (31 - (b & 31))));
-            double Tk = fma((double)(k + 1), po, (double)nc * dpa);
-            if (kp <= k) Tk += dpp;
-            const double Ek = Tk * (EC * (double)(k + 2));
-            const uint32_t bp = T.ballot(valid && (Tk + Ek >= u));
-            if (bp) {
-              const int f = __ffs(bp) - 1;
-              const bool sure = T.shfl((Tk - Ek >= u) ? 1 : 0, f) != 0;
-              if (sure) choice = (wsel << 5) + r0 + f; else replay = true;
-              decided = true;
-            }
-          }
-          if (!decided) replay = true;                               // rounding at the word boundary
-        }
-      }
-      if (replay) {
-        choice = replay_exact<G>(bm, has_prev, nwords, d, kp, fa, fo, fp, u);
-        ++st_replays;
-      }
-      if (choice == d) ++st_overflow;
-      T.sync();                                                       // bitmap is rewritten by the next step
+      const uint32_t choice = uw_step<G>(T, P, C, crow, d, prow, pdeg, prev, has_prev, u, bm, st_replays, st_overflow);
 
       const uint32_t nxt = __ldg(crow + choice);                      // unchecked, as pecanpy.py:559
       if (T.tl == (j & (G - 1))) myval = nxt;
@@ -267,6 +282,137 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_kernel(const WalkPar
     if (st_replays) atomicAdd((unsigned long long*)&P.stats->exact_replays, (unsigned long long)st_replays);
     if (st_overflow) atomicAdd((unsigned long long*)&P.stats->overflow_choices, (unsigned long long)st_overflow);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Cooperative variant for G < 32.  Small groups keep 32/G walkers per warp in flight and share every
+// instruction of the (dominant) short steps, but a hub row handled by G lanes alone would stall the other
+// groups of the warp.  Here the warp runs an explicit per-group state machine in lockstep; each iteration
+//   1. groups without a walker fetch the next row (or retire),
+//   2. steps that touch a long row (deg(cur) or deg(prev) > BIG) are executed ONE AT A TIME BY ALL 32 LANES
+//      (the owner's state is broadcast with full-warp shuffles, uw_step<32> runs, the owner keeps the result),
+//   3. all remaining (short) steps run concurrently, one per group, with uw_step<G>.
+// Results are identical to every other kernel (same Philox counters, same exact arithmetic).
+template <int G, int MINB>
+__global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_coop_kernel(const WalkParams P, const UwConsts C,
+                                                                        const uint32_t BIG) {
+  static_assert(G < 32, "the cooperative kernel is for sub-warp groups");
+  constexpr int GROUPS = UW_THREADS / G;
+  constexpr int WARPS = UW_THREADS / 32;
+  constexpr int SMALL_WORDS = 4;                                      // short steps: deg(cur) <= BIG <= 128
+  __shared__ uint32_t s_bm[GROUPS][SMALL_WORDS];
+  __shared__ uint32_t s_wbm[WARPS][UW_BW];
+  const Tile<G> T;
+  const Tile<32> TW;
+  const int gib = threadIdx.x / G;
+  const int wib = threadIdx.x >> 5;
+  const uint32_t wgid = blockIdx.x * WARPS + wib;                     // global warp id
+  uint32_t* const gbm = C.gbm + (size_t)wgid * C.gbm_stride;          // long-row bitmap scratch of this warp
+  const uint32_t L = P.L;
+  const uint32_t gmask = T.mask;
+  uint32_t st_steps = 0, st_replays = 0, st_overflow = 0;
+
+  bool have = false, done = false;
+  unsigned long long i = 0;
+  uint32_t* out = nullptr;
+  uint32_t cur = 0, prev = 0, pdeg = 0, cs = 0, ce = 0, eff = 0, myval = 0, j = 1;
+  const uint32_t* prow = P.indices;
+  double my_u = 0.0;
+
+  auto finish = [&]() {
+    // tail: the G-block holding entry j (first entry not produced), then zeros, then eff at L+1
+    const uint32_t blk = j & ~(uint32_t)(G - 1);
+    for (uint32_t b0 = blk; b0 < L + 2; b0 += G) {
+      const uint32_t e = b0 + T.tl;
+      uint32_t v = (b0 == blk) ? myval : 0u;
+      if (e == L + 1) v = eff;
+      if (e < L + 2) out[e] = v;
+    }
+    have = false;
+  };
+
+  for (;;) {
+    if (!have && !done) {
+      unsigned long long r = 0;
+      if (T.tl == 0) r = atomicAdd(P.counter, 1ull);
+      r = T.shfl(r, 0);
+      if (r >= P.n_rows) {
+        done = true;
+      } else {
+        i = r;
+        out = P.out + i * P.ld_out;
+        cur = __ldg(P.start + i);
+        prev = 0; pdeg = 0; prow = P.indices;
+        cs = __ldg(P.indptr + cur);
+        ce = __ldg(P.indptr + cur + 1);
+        eff = L + 1;
+        myval = (T.tl == 0) ? cur : 0u;
+        j = 1;
+        have = true;
+      }
+    }
+    if (__all_sync(B2W_FULL, done)) break;
+    uint32_t d = have ? ce - cs : 0u;
+    if (have && d == 0) { eff = j; finish(); }                         // dead end (pecanpy.py:194-196, 204-206)
+    const bool active = have;
+    if (active && ((j - 1) & (G - 1)) == 0) {
+      const uint32_t sj = j + T.tl;
+      if (sj <= L) my_u = step_uniform(P, i, sj);
+    }
+    const double u = T.shfl(my_u, (j - 1) & (G - 1));
+    const bool has_prev = j > 1;
+    const uint32_t* const crow = P.indices + cs;
+    const bool big = active && (d > BIG || (has_prev && pdeg > BIG));
+    uint32_t bigm = __ballot_sync(B2W_FULL, big);
+    uint32_t choice = 0, rep = 0, ovf = 0;
+    while (bigm) {                                                    // warp-uniform loop
+      const int src = __ffs(bigm) - 1;                                // a lane of the owning group
+      const uint32_t b_cs = __shfl_sync(B2W_FULL, cs, src);
+      const uint32_t b_d = __shfl_sync(B2W_FULL, d, src);
+      const unsigned long long b_prow = __shfl_sync(B2W_FULL, (unsigned long long)(uintptr_t)prow, src);
+      const uint32_t b_pdeg = __shfl_sync(B2W_FULL, pdeg, src);
+      const uint32_t b_prev = __shfl_sync(B2W_FULL, prev, src);
+      const bool b_hp = __shfl_sync(B2W_FULL, j, src) > 1;
+      const double b_u = __shfl_sync(B2W_FULL, u, src);
+      uint32_t* const bmw = (((b_d + 31) >> 5) <= (uint32_t)UW_BW) ? s_wbm[wib] : gbm;
+      uint32_t r2 = 0, o2 = 0;
+      const uint32_t c = uw_step<32>(TW, P, C, P.indices + b_cs, b_d, reinterpret_cast<const uint32_t*>((uintptr_t)b_prow),
+                                     b_pdeg, b_prev, b_hp, b_u, bmw, r2, o2);
+      const uint32_t om = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << (src & ~(G - 1)));
+      if (gmask == om) { choice = c; rep = r2; ovf = o2; }
+      bigm &= ~om;
+    }
+    if (active && !big) choice = uw_step<G>(T, P, C, crow, d, prow, pdeg, prev, has_prev, u, s_bm[gib], rep, ovf);
+    if (active) {
+      st_replays += rep; st_overflow += ovf;
+      const uint32_t nxt = __ldg(crow + choice);                      // unchecked, as pecanpy.py:559
+      if (T.tl == (j & (G - 1))) myval = nxt;
+      if ((j & (G - 1)) == G - 1) {
+        out[(j & ~(uint32_t)(G - 1)) + T.tl] = myval;
+        myval = 0u;
+      }
+      prev = cur; prow = crow; pdeg = d;
+      cur = nxt;
+      cs = __ldg(P.indptr + cur);
+      ce = __ldg(P.indptr + cur + 1);
+      ++st_steps;
+      ++j;
+      if (j > L) finish();
+    }
+  }
+  if (P.stats && !(P.flags & B2W_FLAG_NO_FILTER_STATS) && T.tl == 0) {
+    if (st_steps) atomicAdd((unsigned long long*)&P.stats->steps, (unsigned long long)st_steps);
+    if (st_replays) atomicAdd((unsigned long long*)&P.stats->exact_replays, (unsigned long long)st_replays);
+    if (st_overflow) atomicAdd((unsigned long long*)&P.stats->overflow_choices, (unsigned long long)st_overflow);
+  }
+}
+
+template <int G, int MINB>
+int grid_blocks_coop(const b2w_graph* g) {
+  int per_sm = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, walk_uw_coop_kernel<G, MINB>, UW_THREADS, 0);
+  if (per_sm < 1) per_sm = 1;
+  return per_sm * g->num_sms;
 }
 
 template <int G, int MINB>
@@ -347,9 +493,23 @@ int b2w_launch_uw(const b2w_graph* g, const WalkParams& P_in, cudaStream_t s) {
     if ((uint64_t)blocks > need) blocks = (int)(need ? need : 1);                    \
     walk_uw_kernel<GG, BB><<<blocks, UW_THREADS, 0, s>>>(P, C);                      \
   } while (0)
-  if (G == 8) B2W_UW_LAUNCH(8, 4);
-  else if (G == 16) { if (MB == 4) B2W_UW_LAUNCH(16, 4); else if (MB == 6) B2W_UW_LAUNCH(16, 6); else B2W_UW_LAUNCH(16, 5); }
+  // G < 32: the cooperative kernel (long rows by the whole warp); bits 20..23 of flags tune BIG = 16 << x
+  const uint32_t bigx = (P.flags >> 20) & 0xF;
+  const uint32_t BIG = bigx ? (16u << (bigx - 1)) : 64u;
+  const bool coop = !(P.flags & B2W_FLAG_NO_COOP);
+#define B2W_UW_COOP(GG, BB)                                                          \
+  do {                                                                               \
+    int blocks = grid_blocks_coop<GG, BB>(g);                                        \
+    if ((uint64_t)blocks > need) blocks = (int)(need ? need : 1);                    \
+    walk_uw_coop_kernel<GG, BB><<<blocks, UW_THREADS, 0, s>>>(P, C, BIG > 128u ? 128u : BIG); \
+  } while (0)
+  if (G == 8) { if (coop) B2W_UW_COOP(8, 4); else B2W_UW_LAUNCH(8, 4); }
+  else if (G == 16) {
+    if (coop) B2W_UW_COOP(16, 4);
+    else if (MB == 4) B2W_UW_LAUNCH(16, 4); else if (MB == 6) B2W_UW_LAUNCH(16, 6); else B2W_UW_LAUNCH(16, 5);
+  }
   else { if (MB == 4) B2W_UW_LAUNCH(32, 4); else if (MB == 6) B2W_UW_LAUNCH(32, 6); else B2W_UW_LAUNCH(32, 5); }   // measured: 5 CTAs/SM (48 regs) best
+#undef B2W_UW_COOP
 #undef B2W_UW_LAUNCH
   return b2w_cuda_fail(cudaGetLastError(), "walk_uw_kernel launch");
 }
