@@ -68,7 +68,7 @@ typedef enum {
 #define B2W_FLAG_THREAD_PER_WALKER 0x4u  /* SparseOTF: use the lane-per-walker kernel */
 #define B2W_FLAG_NO_UNWEIGHTED_KERNEL 0x8u /* SparseOTF: always use the generic (weight-streaming) kernel */
 #define B2W_FLAG_NO_TMA 0x10u /* DenseOTF: per-lane vector loads instead of cp.async.bulk staging */
-#define B2W_FLAG_NO_COOP 0x20u /* unweighted SparseOTF, G < 32: plain per-group kernel (no warp-cooperative long rows) */
+#define B2W_FLAG_COOP 0x20u /* unweighted SparseOTF, G < 32: warp-cooperative state-machine kernel (long rows by all 32 lanes) */
 #define B2W_FLAG_GROUP(n) (((uint32_t)(n) & 0xFFu) << 8) /* tuning: lanes per walker (8/16/32), 0 = auto */
 
 typedef struct b2w_graph b2w_graph; /* opaque */

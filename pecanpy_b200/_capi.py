@@ -19,7 +19,7 @@ FLAG_NO_FILTER_STATS = 0x2
 FLAG_THREAD_PER_WALKER = 0x4
 FLAG_NO_UNWEIGHTED_KERNEL = 0x8
 FLAG_NO_TMA = 0x10
-FLAG_NO_COOP = 0x20
+FLAG_COOP = 0x20
 
 
 def FLAG_GROUP(n: int) -> int:

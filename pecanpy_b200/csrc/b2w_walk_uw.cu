@@ -427,9 +427,9 @@ int pick_group(const b2w_graph* g, uint32_t flags) {
   uint32_t forced = (flags >> 8) & 0xFF;                             // debug/tuning: bits 8..15 = group size
   if (forced == 8 || forced == 16 || forced == 32) return (int)forced;
   double avg = g->n ? (double)g->nnz / g->n : 0.0;
-  // measured (B200): 16 lanes per walker win on flat low-degree graphs (ER, deg 20: 3.29 vs 2.99 G steps/s),
-  // 32 lanes win as soon as there are hub rows (power law: 1.77 vs 1.44)
-  return (avg <= 32.0 && (double)g->max_degree <= 8.0 * avg + 16.0) ? 16 : 32;
+  // measured (B200): 8 lanes per walker win on flat low-degree graphs (ER, deg 20: 3.72 / 3.44 / 2.97 G steps/s
+  // for 8 / 16 / 32 lanes), 32 lanes win as soon as there are hub rows (power law: 1.77 vs 1.39 for 16)
+  return (avg <= 32.0 && (double)g->max_degree <= 8.0 * avg + 16.0) ? 8 : 32;
 }
 
 uint32_t max_groups(const b2w_graph* g) {
@@ -493,10 +493,10 @@ int b2w_launch_uw(const b2w_graph* g, const WalkParams& P_in, cudaStream_t s) {
     if ((uint64_t)blocks > need) blocks = (int)(need ? need : 1);                    \
     walk_uw_kernel<GG, BB><<<blocks, UW_THREADS, 0, s>>>(P, C);                      \
   } while (0)
-  // G < 32: the cooperative kernel (long rows by the whole warp); bits 20..23 of flags tune BIG = 16 << x
+  // G < 32 with B2W_FLAG_COOP: the cooperative kernel (long rows by the whole warp); bits 20..23 tune BIG = 16 << x
   const uint32_t bigx = (P.flags >> 20) & 0xF;
   const uint32_t BIG = bigx ? (16u << (bigx - 1)) : 64u;
-  const bool coop = !(P.flags & B2W_FLAG_NO_COOP);
+  const bool coop = (P.flags & B2W_FLAG_COOP) != 0;   // opt-in: measured slower than the plain kernels
 #define B2W_UW_COOP(GG, BB)                                                          \
   do {                                                                               \
     int blocks = grid_blocks_coop<GG, BB>(g);                                        \
