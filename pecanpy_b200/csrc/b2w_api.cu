@@ -2,9 +2,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
-#include <vector>
 #include <mutex>
 #include <new>
 
@@ -78,78 +76,6 @@ __global__ void dense_check_kernel(uint64_t total, const double* __restrict__ da
   }
   if (bad_weight) atomicOr(&res->bad_weight, 1u);
   if (bad_mask) atomicOr(&res->bad_order, 1u);
-}
-
-// ---------------------------------------------------------------- hub index
-// One warp per hub row: insert (neighbour id -> position) with linear probing.
-__global__ void hub_build_kernel(const uint32_t* __restrict__ hubs, uint32_t n_hubs, const uint32_t* __restrict__ indptr,
-                                 const uint32_t* __restrict__ indices, const unsigned long long* __restrict__ desc,
-                                 uint32_t* __restrict__ keys, uint32_t* __restrict__ pos) {
-  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= n_hubs) return;
-  const uint32_t node = hubs[w];
-  const uint32_t cs = indptr[node], deg = indptr[node + 1] - cs;
-  const unsigned long long dsc = desc[node];
-  const uint32_t lg = (uint32_t)(dsc & 63ull);
-  const unsigned long long off = dsc >> 6;
-  const uint32_t mask = (1u << lg) - 1u;
-  for (uint32_t k = lane; k < deg; k += 32) {
-    const uint32_t y = indices[cs + k];
-    uint32_t slot = (y * 2654435761u) >> (32 - lg);
-    for (;;) {
-      const uint32_t old = atomicCAS(&keys[off + slot], 0xFFFFFFFFu, y);
-      if (old == 0xFFFFFFFFu) { pos[off + slot] = k; break; }
-      slot = (slot + 1) & mask;
-    }
-  }
-}
-
-static void hub_index_free(b2w_graph* g) {
-  if (g->hub_desc) cudaFree(g->hub_desc);
-  if (g->hub_keys) cudaFree(g->hub_keys);
-  if (g->hub_pos) cudaFree(g->hub_pos);
-  g->hub_desc = nullptr; g->hub_keys = nullptr; g->hub_pos = nullptr; g->hub_slots = 0;
-}
-
-// Rows of degree >= hub_min get a hash table of 2^ceil(log2(2 deg)) slots (load factor <= 0.5).
-static int hub_index_build(b2w_graph* g) {
-  uint32_t hub_min = 256;
-  if (const char* e = getenv("B2W_HUB_MIN")) hub_min = (uint32_t)strtoul(e, nullptr, 10);
-  g->hub_min = hub_min;
-  if (hub_min == 0 || g->max_degree < hub_min || hub_min < 2) return B2W_OK;
-  std::vector<uint32_t> indptr((size_t)g->n + 1);
-  B2W_CUDA(cudaMemcpy(indptr.data(), g->indptr, ((size_t)g->n + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-  std::vector<unsigned long long> desc(g->n, 0ull);
-  std::vector<uint32_t> hubs;
-  unsigned long long slots = 0;
-  for (uint32_t i = 0; i < g->n; ++i) {
-    const uint32_t deg = indptr[i + 1] - indptr[i];
-    if (deg < hub_min) continue;
-    uint32_t lg = 1;
-    while ((1ull << lg) < 2ull * deg) ++lg;
-    desc[i] = (slots << 6) | lg;
-    slots += 1ull << lg;
-    hubs.push_back(i);
-  }
-  if (hubs.empty()) return B2W_OK;
-  uint32_t* d_hubs = nullptr;
-  cudaError_t e = cudaMalloc(&g->hub_desc, (size_t)g->n * sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMalloc(&g->hub_keys, slots * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&g->hub_pos, slots * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&d_hubs, hubs.size() * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMemcpy(g->hub_desc, desc.data(), (size_t)g->n * sizeof(unsigned long long), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(d_hubs, hubs.data(), hubs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemset(g->hub_keys, 0xFF, slots * sizeof(uint32_t));
-  if (e == cudaSuccess) {
-    const uint32_t nh = (uint32_t)hubs.size();
-    hub_build_kernel<<<(nh * 32 + 255) / 256, 256>>>(d_hubs, nh, g->indptr, g->indices, g->hub_desc, g->hub_keys, g->hub_pos);
-    e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaDeviceSynchronize();
-  }
-  if (d_hubs) cudaFree(d_hubs);
-  if (e != cudaSuccess) { hub_index_free(g); return b2w_cuda_fail(e, "hub index build"); }
-  g->hub_slots = slots;
-  return B2W_OK;
 }
 
 // Staging state of b2w_walk_host, cached in the handle so that repeated calls do not pay
@@ -256,8 +182,6 @@ extern "C" int b2w_graph_csr_create(int device, uint32_t n, uint64_t nnz, const 
   }
   g->max_degree = h.max_degree;
   if (!h.not_unweighted) g->flags |= B2W_GRAPH_UNWEIGHTED;
-  rc = hub_index_build(g);
-  if (rc) { b2w_host_pipe_destroy(g->pipe); delete g; return rc; }
   *out = g;
   return B2W_OK;
 }
@@ -295,7 +219,6 @@ extern "C" int b2w_graph_info_get(const b2w_graph* g, b2w_graph_info* out) {
 extern "C" void b2w_graph_destroy(b2w_graph* g) {
   if (!g) return;
   cudaSetDevice(g->device);
-  hub_index_free(g);
   b2w_host_pipe_destroy(g->pipe);
   delete g;
 }
@@ -375,7 +298,6 @@ extern "C" int b2w_walk(const b2w_graph* g, int mode, double p, double q, int ex
   P.n = g->n; P.indptr = g->indptr; P.indices = g->indices; P.data = g->data;
   P.dense = g->dense; P.nonzero = g->nonzero; P.thr = d_thr;
   P.alias_indptr = g->alias_indptr; P.alias_j = g->alias_j; P.alias_q = g->alias_q;
-  if (!(flags & B2W_FLAG_NO_HUB_INDEX)) { P.hub_desc = g->hub_desc; P.hub_keys = g->hub_keys; P.hub_pos = g->hub_pos; }
   P.start = d_start; P.feed = d_feed; P.out = d_out; P.ld_out = ld_out;
   P.row0 = row0; P.n_rows = n_rows; P.L = walk_length;
   P.key0 = (uint32_t)seed; P.key1 = (uint32_t)(seed >> 32);

@@ -27,13 +27,6 @@ struct b2w_graph {
   const uint64_t* alias_indptr;
   const uint32_t* alias_j;
   const float* alias_q;
-  // hub index (owned by the handle): an open-addressing hash table per row of degree >= hub_min mapping
-  // neighbour id -> position in the row, so membership in a hub row costs ~2 probes instead of log2(deg)
-  unsigned long long* hub_desc;   // [n] 0 = no table, else (offset << 6) | log2(slots)
-  uint32_t* hub_keys;             // [hub_slots] neighbour id or 0xFFFFFFFF
-  uint32_t* hub_pos;              // [hub_slots] position of that neighbour in its row
-  uint64_t hub_slots;
-  uint32_t hub_min;
   // staging buffers / streams of b2w_walk_host (lazily allocated, guarded by their own mutex)
   b2w_host_pipe* pipe;
 };
@@ -50,9 +43,6 @@ struct WalkParams {
   const uint64_t* __restrict__ alias_indptr;
   const uint32_t* __restrict__ alias_j;
   const float* __restrict__ alias_q;
-  const unsigned long long* __restrict__ hub_desc;
-  const uint32_t* __restrict__ hub_keys;
-  const uint32_t* __restrict__ hub_pos;
   const uint32_t* __restrict__ start;
   const double* __restrict__ feed;
   uint32_t* __restrict__ out;

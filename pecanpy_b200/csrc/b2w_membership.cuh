@@ -69,82 +69,17 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__
 // `prev` itself never counts as common (rw/sparse_rw.py:84); its position is returned in `kp`
 // (B2W_NONE when prev is not a neighbour of cur: directed graphs, or after a choice == deg overflow).
 // Returns the number of common neighbours.  Ends with a group sync: the bitmap is visible to all lanes.
-// Hub index lookup: position of `y` in the row described by `desc` (see b2w_graph::hub_desc), or B2W_NONE.
-__device__ __forceinline__ uint32_t hub_hash(uint32_t y) { return y * 2654435761u; }
-
-__device__ __forceinline__ uint32_t hub_lookup(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ pos,
-                                               const unsigned long long desc, const uint32_t y) {
-  const uint32_t lg = (uint32_t)(desc & 63ull);
-  const unsigned long long off = desc >> 6;
-  const uint32_t mask = (1u << lg) - 1u;
-  uint32_t slot = hub_hash(y) >> (32 - lg);
-  for (;;) {
-    const uint32_t k = __ldg(keys + off + slot);
-    if (k == y) return __ldg(pos + off + slot);
-    if (k == B2W_NONE) return B2W_NONE;
-    slot = (slot + 1) & mask;
-  }
-}
-
-struct HubIndex {
-  const uint32_t* __restrict__ keys;
-  const uint32_t* __restrict__ pos;
-  unsigned long long cdesc, pdesc;   // descriptors of row(cur) and row(prev); 0 = no table
-};
-
 template <int G>
 __device__ __forceinline__ uint32_t membership_bitmap(const Tile<G>& T, const uint32_t* __restrict__ crow,
                                                       const uint32_t d, const uint32_t* __restrict__ prow,
                                                       const uint32_t pdeg, const uint32_t prev,
-                                                      uint32_t* __restrict__ bm, const HubIndex& H, uint32_t& kp) {
+                                                      uint32_t* __restrict__ bm, uint32_t& kp) {
   const uint32_t nwords = (d + 31) >> 5;
-  uint32_t m = 0;
-  kp = B2W_NONE;
-  // ---- hub index: whichever long row has a table is probed with the other row's elements as keys
-  if (H.pdesc != 0ull && (H.cdesc == 0ull || d <= pdeg)) {
-    // keys = neighbours of cur (streamed), table = row(prev): forward, whole bitmap words are written
-    for (uint32_t c0 = 0; c0 < d; c0 += G) {
-      const uint32_t k = c0 + T.tl;
-      const bool valid = k < d;
-      const uint32_t x = valid ? __ldg(crow + k) : B2W_NONE;
-      const bool found = valid && hub_lookup(H.keys, H.pos, H.pdesc, x) != B2W_NONE;
-      const bool isprev = valid && (x == prev);
-      const uint32_t bprev = T.ballot(isprev);
-      if (bprev) kp = c0 + __ffs(bprev) - 1;
-      const uint32_t bal = T.ballot(found && !isprev);
-      if (T.tl == 0) {
-        if (G == 32 || (c0 & 31) == 0) bm[c0 >> 5] = bal; else bm[c0 >> 5] |= bal << (c0 & 31);
-      }
-      m += __popc(bal);
-    }
-    T.sync();
-    return m;
-  }
-  if (H.cdesc != 0ull) {
-    // keys = neighbours of prev and prev itself, table = row(cur): reverse, needs the bitmap zeroed
-    for (uint32_t w = T.tl; w < nwords; w += G) bm[w] = 0u;
-    T.sync();
-    const uint32_t nkeys = pdeg + 1;
-    uint32_t mloc = 0, kploc = B2W_NONE;
-    for (uint32_t c0 = 0; c0 < nkeys; c0 += G) {
-      const uint32_t ii = c0 + T.tl;
-      if (ii < nkeys) {
-        const uint32_t y = ii < pdeg ? __ldg(prow + ii) : prev;
-        const uint32_t pos = hub_lookup(H.keys, H.pos, H.cdesc, y);
-        if (pos != B2W_NONE) {
-          if (ii == pdeg) kploc = pos;
-          else if (y != prev) { atomicOr(&bm[pos >> 5], 1u << (pos & 31)); ++mloc; }
-        }
-      }
-    }
-    m = T.sum(mloc);
-    kp = T.minu(kploc);
-    T.sync();
-    return m;
-  }
   const uint32_t lgp = 32 - __clz(pdeg), lgd = 32 - __clz(d);
   const uint32_t fwd_cost = ((d + G - 1) / G) * (lgp + 2);
   const uint32_t rev_cost = ((pdeg + G) / G) * (lgd + 2) + (nwords + G - 1) / G;
+  uint32_t m = 0;
+  kp = B2W_NONE;
   // rows of cur that fit a few chunks always take the forward direction: the choice then does not depend on
   // deg(prev), so the groups of one warp stay on the same path (no divergence between walkers)
   if (d <= 2 * 32 || fwd_cost <= rev_cost) {

@@ -132,12 +132,12 @@ __device__ __forceinline__ uint32_t uw_step(const Tile<G>& T, const WalkParams& 
                                             const uint32_t* __restrict__ crow, const uint32_t d,
                                             const uint32_t* __restrict__ prow, const uint32_t pdeg, const uint32_t prev,
                                             const bool has_prev, const double u, uint32_t* __restrict__ bm,
-                                            const HubIndex& H, uint32_t& st_replays, uint32_t& st_overflow) {
+                                            uint32_t& st_replays, uint32_t& st_overflow) {
   const double EC = 1.01 * 5.9604644775390625e-08;                    // 1.01 * 2^-24
   const uint32_t nwords = (d + 31) >> 5;
   // ---------------- phase 1: membership bitmap over the positions of row(cur)
   uint32_t m = 0, kp = NONE;
-  if (has_prev) m = membership_bitmap<G>(T, crow, d, prow, pdeg, prev, bm, H, kp);
+  if (has_prev) m = membership_bitmap<G>(T, crow, d, prow, pdeg, prev, bm, kp);
 
   // ---------------- phase 2: exact normaliser, three-valued probabilities
   const float w_o = has_prev ? C.w_out : 1.0f;                    // first step: every weight is 1
@@ -237,7 +237,6 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_kernel(const WalkPar
     const uint32_t* prow = P.indices;
     uint32_t cs = __ldg(P.indptr + cur);
     uint32_t ce = __ldg(P.indptr + cur + 1);
-    HubIndex H = {P.hub_keys, P.hub_pos, P.hub_desc ? __ldg(P.hub_desc + cur) : 0ull, 0ull};
     uint32_t eff = L + 1;
     uint32_t myval = (T.tl == 0) ? cur : 0u;                          // lane (e mod G) holds output entry e
     double my_u = 0.0;
@@ -255,7 +254,7 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_kernel(const WalkPar
       uint32_t* const bm = (nwords <= UW_BW) ? s_bm[gib] : gbm;
       const uint32_t* const crow = P.indices + cs;
 
-      const uint32_t choice = uw_step<G>(T, P, C, crow, d, prow, pdeg, prev, has_prev, u, bm, H, st_replays, st_overflow);
+      const uint32_t choice = uw_step<G>(T, P, C, crow, d, prow, pdeg, prev, has_prev, u, bm, st_replays, st_overflow);
 
       const uint32_t nxt = __ldg(crow + choice);                      // unchecked, as pecanpy.py:559
       if (T.tl == (j & (G - 1))) myval = nxt;
@@ -267,8 +266,6 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_kernel(const WalkPar
       cur = nxt;
       cs = __ldg(P.indptr + cur);
       ce = __ldg(P.indptr + cur + 1);
-      H.pdesc = H.cdesc;
-      H.cdesc = P.hub_desc ? __ldg(P.hub_desc + cur) : 0ull;
       ++st_steps;
     }
     // tail: the G-block holding entry j (first entry not produced), then zeros, then eff at L+1
@@ -321,7 +318,6 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_coop_kernel(const Wa
   uint32_t cur = 0, prev = 0, pdeg = 0, cs = 0, ce = 0, eff = 0, myval = 0, j = 1;
   const uint32_t* prow = P.indices;
   double my_u = 0.0;
-  HubIndex H = {P.hub_keys, P.hub_pos, 0ull, 0ull};
 
   auto finish = [&]() {
     // tail: the G-block holding entry j (first entry not produced), then zeros, then eff at L+1
@@ -349,8 +345,6 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_coop_kernel(const Wa
         prev = 0; pdeg = 0; prow = P.indices;
         cs = __ldg(P.indptr + cur);
         ce = __ldg(P.indptr + cur + 1);
-        H.cdesc = P.hub_desc ? __ldg(P.hub_desc + cur) : 0ull;
-        H.pdesc = 0ull;
         eff = L + 1;
         myval = (T.tl == 0) ? cur : 0u;
         j = 1;
@@ -380,16 +374,15 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_coop_kernel(const Wa
       const uint32_t b_prev = __shfl_sync(B2W_FULL, prev, src);
       const bool b_hp = __shfl_sync(B2W_FULL, j, src) > 1;
       const double b_u = __shfl_sync(B2W_FULL, u, src);
-      const HubIndex bH = {P.hub_keys, P.hub_pos, __shfl_sync(B2W_FULL, H.cdesc, src), __shfl_sync(B2W_FULL, H.pdesc, src)};
       uint32_t* const bmw = (((b_d + 31) >> 5) <= (uint32_t)UW_BW) ? s_wbm[wib] : gbm;
       uint32_t r2 = 0, o2 = 0;
       const uint32_t c = uw_step<32>(TW, P, C, P.indices + b_cs, b_d, reinterpret_cast<const uint32_t*>((uintptr_t)b_prow),
-                                     b_pdeg, b_prev, b_hp, b_u, bmw, bH, r2, o2);
+                                     b_pdeg, b_prev, b_hp, b_u, bmw, r2, o2);
       const uint32_t om = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << (src & ~(G - 1)));
       if (gmask == om) { choice = c; rep = r2; ovf = o2; }
       bigm &= ~om;
     }
-    if (active && !big) choice = uw_step<G>(T, P, C, crow, d, prow, pdeg, prev, has_prev, u, s_bm[gib], H, rep, ovf);
+    if (active && !big) choice = uw_step<G>(T, P, C, crow, d, prow, pdeg, prev, has_prev, u, s_bm[gib], rep, ovf);
     if (active) {
       st_replays += rep; st_overflow += ovf;
       const uint32_t nxt = __ldg(crow + choice);                      // unchecked, as pecanpy.py:559
@@ -402,8 +395,6 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_coop_kernel(const Wa
       cur = nxt;
       cs = __ldg(P.indptr + cur);
       ce = __ldg(P.indptr + cur + 1);
-      H.pdesc = H.cdesc;
-      H.cdesc = P.hub_desc ? __ldg(P.hub_desc + cur) : 0ull;
       ++st_steps;
       ++j;
       if (j > L) finish();

@@ -69,11 +69,7 @@ __device__ __forceinline__ uint32_t otf_choice_warp(const WalkParams& P, const T
 
   // ---- phase 1: membership (node2vec)
   uint32_t kp = B2W_NONE;
-  if (!EXTEND && has_prev) {
-    const HubIndex H = {P.hub_keys, P.hub_pos, P.hub_desc ? __ldg(P.hub_desc + cur) : 0ull,
-                        P.hub_desc ? __ldg(P.hub_desc + prev) : 0ull};
-    membership_bitmap<32>(T, crow, d, prow, pdeg, prev, bm, H, kp);
-  }
+  if (!EXTEND && has_prev) membership_bitmap<32>(T, crow, d, prow, pdeg, prev, bm, kp);
 
   // ---- phase 2: stream the weights, stage w, one partial sum per chunk
   const uint32_t lgp = 32 - __clz(pdeg);
