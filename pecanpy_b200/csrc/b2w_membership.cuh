@@ -68,12 +68,14 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__
 //            O(deg(prev) log deg(cur)) words of row(cur); needs the bitmap zeroed first)
 // `prev` itself never counts as common (rw/sparse_rw.py:84); its position is returned in `kp`
 // (B2W_NONE when prev is not a neighbour of cur: directed graphs, or after a choice == deg overflow).
-// Returns the number of common neighbours.  Ends with a group sync: the bitmap is visible to all lanes.
+// Returns the number of common neighbours.  Rows of at most 32 entries return their single bitmap word in
+// `word0` (in_regs = true, nothing written to `bm`); otherwise the bitmap is in `bm` and the function ends with a
+// group sync so that it is visible to all lanes.
 template <int G>
 __device__ __forceinline__ uint32_t membership_bitmap(const Tile<G>& T, const uint32_t* __restrict__ crow,
                                                       const uint32_t d, const uint32_t* __restrict__ prow,
                                                       const uint32_t pdeg, const uint32_t prev,
-                                                      uint32_t* __restrict__ bm, uint32_t& kp) {
+                                                      uint32_t* __restrict__ bm, uint32_t& kp, uint32_t& word0, bool& in_regs) {
   const uint32_t nwords = (d + 31) >> 5;
   const uint32_t lgp = 32 - __clz(pdeg), lgd = 32 - __clz(d);
   const uint32_t fwd_cost = ((d + G - 1) / G) * (lgp + 2);
@@ -82,6 +84,27 @@ __device__ __forceinline__ uint32_t membership_bitmap(const Tile<G>& T, const ui
   kp = B2W_NONE;
   // rows of cur that fit a few chunks always take the forward direction: the choice then does not depend on
   // deg(prev), so the groups of one warp stay on the same path (no divergence between walkers)
+  word0 = 0u;
+  in_regs = false;
+  if (d <= 32) {
+    // single-word row (the common case): the bitmap stays in a register -- no shared-memory store, no group
+    // sync; the caller materialises it only if it has to replay
+    for (uint32_t c0 = 0; c0 < d; c0 += G) {
+      const uint32_t k = c0 + T.tl;
+      const bool valid = k < d;
+      const uint32_t x = valid ? __ldg(crow + k) : B2W_NONE;
+      const uint32_t pos = lower_bound_u32(prow, pdeg, x, lgp);
+      const bool found = pos < pdeg && __ldg(prow + pos) == x;
+      const bool isprev = valid && (x == prev);
+      const uint32_t bprev = T.ballot(isprev);
+      if (bprev) kp = c0 + __ffs(bprev) - 1;
+      const uint32_t bal = T.ballot(valid && found && !isprev);
+      word0 |= (G == 32) ? bal : (bal << c0);
+      m += __popc(bal);
+    }
+    in_regs = true;
+    return m;
+  }
   if (d <= 2 * 32 || fwd_cost <= rev_cost) {
     for (uint32_t c0 = 0; c0 < d; c0 += G) {
       const uint32_t k = c0 + T.tl;

@@ -136,8 +136,9 @@ __device__ __forceinline__ uint32_t uw_step(const Tile<G>& T, const WalkParams& 
   const double EC = 1.01 * 5.9604644775390625e-08;                    // 1.01 * 2^-24
   const uint32_t nwords = (d + 31) >> 5;
   // ---------------- phase 1: membership bitmap over the positions of row(cur)
-  uint32_t m = 0, kp = NONE;
-  if (has_prev) m = membership_bitmap<G>(T, crow, d, prow, pdeg, prev, bm, kp);
+  uint32_t m = 0, kp = NONE, word0 = 0;
+  bool in_regs = false;
+  if (has_prev) m = membership_bitmap<G>(T, crow, d, prow, pdeg, prev, bm, kp, word0, in_regs);
 
   // ---------------- phase 2: exact normaliser, three-valued probabilities
   const float w_o = has_prev ? C.w_out : 1.0f;                    // first step: every weight is 1
@@ -180,7 +181,7 @@ __device__ __forceinline__ uint32_t uw_step(const Tile<G>& T, const WalkParams& 
         carry = T.shfl(incl, G - 1);
       }
     } else if (has_prev) {
-      bits_sel = bm[0];
+      bits_sel = in_regs ? word0 : bm[0];
     }
     if (wsel != NONE) {
       // position level inside the selected word
@@ -206,11 +207,12 @@ __device__ __forceinline__ uint32_t uw_step(const Tile<G>& T, const WalkParams& 
     }
   }
   if (replay) {
+    if (in_regs) { if (T.tl == 0) bm[0] = word0; T.sync(); }      // the replay reads the bitmap from memory
     choice = replay_exact<G>(bm, has_prev, nwords, d, kp, fa, fo, fp, u);
     ++st_replays;
   }
   if (choice == d) ++st_overflow;
-  T.sync();                                                       // bitmap is rewritten by the next step
+  if (!in_regs || replay) T.sync();                               // a bitmap in memory is rewritten by the next step
 
   return choice;
 }

@@ -69,7 +69,12 @@ __device__ __forceinline__ uint32_t otf_choice_warp(const WalkParams& P, const T
 
   // ---- phase 1: membership (node2vec)
   uint32_t kp = B2W_NONE;
-  if (!EXTEND && has_prev) membership_bitmap<32>(T, crow, d, prow, pdeg, prev, bm, kp);
+  if (!EXTEND && has_prev) {
+    uint32_t word0 = 0;
+    bool in_regs = false;
+    membership_bitmap<32>(T, crow, d, prow, pdeg, prev, bm, kp, word0, in_regs);
+    if (in_regs) { if (lane == 0) bm[0] = word0; __syncwarp(); }
+  }
 
   // ---- phase 2: stream the weights, stage w, one partial sum per chunk
   const uint32_t lgp = 32 - __clz(pdeg);
