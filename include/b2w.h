@@ -69,7 +69,6 @@ typedef enum {
 #define B2W_FLAG_NO_UNWEIGHTED_KERNEL 0x8u /* SparseOTF: always use the generic (weight-streaming) kernel */
 #define B2W_FLAG_NO_TMA 0x10u /* DenseOTF: per-lane vector loads instead of cp.async.bulk staging */
 #define B2W_FLAG_COOP 0x20u /* unweighted SparseOTF, G < 32: warp-cooperative state-machine kernel (long rows by all 32 lanes) */
-#define B2W_FLAG_NO_HUB_FILTER 0x40u /* SparseOTF node2vec: ignore the per-hub-row Bloom pre-filter */
 #define B2W_FLAG_GROUP(n) (((uint32_t)(n) & 0xFFu) << 8) /* tuning: lanes per walker (8/16/32), 0 = auto */
 
 typedef struct b2w_graph b2w_graph; /* opaque */
@@ -104,9 +103,7 @@ int b2w_device_count(int* out);
  * when the reference's unchecked `indices[indptr[cur] + choice]` (pecanpy.py:559) is hit with
  * choice == degree on the last non-empty row; set it to 0.
  * Validation (sortedness, uniqueness, weights finite and >= 0) runs on the device and
- * synchronises the stream once.  For rows of degree >= 128 (env B2W_BLOOM_MIN, 0 = off) the handle also builds
- * and owns a blocked Bloom filter of the row's neighbour ids (2-4 bytes per neighbour; a pre-filter for the
- * membership searches of the SparseOTF kernels, it never changes a result).  Replaces: SparseGraph members read as closure constants in
+ * synchronises the stream once.  Replaces: SparseGraph members read as closure constants in
  * pecanpy.py:397-399,535-537. */
 int b2w_graph_csr_create(int device, uint32_t num_nodes, uint64_t nnz, const uint32_t* d_indptr,
                          const uint32_t* d_indices, const float* d_data, b2w_graph** out);

@@ -20,7 +20,6 @@ FLAG_THREAD_PER_WALKER = 0x4
 FLAG_NO_UNWEIGHTED_KERNEL = 0x8
 FLAG_NO_TMA = 0x10
 FLAG_COOP = 0x20
-FLAG_NO_HUB_FILTER = 0x40
 
 
 def FLAG_GROUP(n: int) -> int:

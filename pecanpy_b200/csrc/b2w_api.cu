@@ -2,13 +2,11 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
-#include <vector>
 #include <mutex>
 #include <new>
 
-#include "b2w_membership.cuh"
+#include "b2w_common.cuh"
 
 // ---------------------------------------------------------------- errors
 static thread_local char g_err[512] = "";
@@ -78,67 +76,6 @@ __global__ void dense_check_kernel(uint64_t total, const double* __restrict__ da
   }
   if (bad_weight) atomicOr(&res->bad_weight, 1u);
   if (bad_mask) atomicOr(&res->bad_order, 1u);
-}
-
-// ---------------------------------------------------------------- hub pre-filter (blocked Bloom)
-__global__ void bloom_build_kernel(const uint32_t* __restrict__ hubs, uint32_t n_hubs, const uint32_t* __restrict__ indptr,
-                                   const uint32_t* __restrict__ indices, const uint32_t* __restrict__ desc,
-                                   unsigned long long* __restrict__ blocks) {
-  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (w >= n_hubs) return;
-  const uint32_t node = hubs[w];
-  const uint32_t cs = indptr[node], deg = indptr[node + 1] - cs;
-  const uint32_t dsc = desc[node], lg = dsc & 31u;
-  unsigned long long* base = blocks + (dsc >> 5);
-  for (uint32_t k = lane; k < deg; k += 32) {
-    const uint32_t y = indices[cs + k];
-    atomicOr(base + (lg ? (bloom_h1(y) >> (32 - lg)) : 0u), bloom_mask(y));
-  }
-}
-
-static void bloom_free(b2w_graph* g) {
-  if (g->bloom_desc) cudaFree(g->bloom_desc);
-  if (g->bloom_blocks) cudaFree(g->bloom_blocks);
-  g->bloom_desc = nullptr; g->bloom_blocks = nullptr; g->bloom_nblocks = 0;
-}
-
-// Rows of degree >= B2W_BLOOM_MIN (default 128, 0 = off) get 2^ceil(log2(deg / 4)) 64-bit blocks.
-static int bloom_build(b2w_graph* g) {
-  uint32_t bmin = 128;
-  if (const char* e = getenv("B2W_BLOOM_MIN")) bmin = (uint32_t)strtoul(e, nullptr, 10);
-  if (bmin == 0 || g->max_degree < bmin) return B2W_OK;
-  std::vector<uint32_t> indptr((size_t)g->n + 1);
-  B2W_CUDA(cudaMemcpy(indptr.data(), g->indptr, ((size_t)g->n + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-  std::vector<uint32_t> desc(g->n, 0u), hubs;
-  unsigned long long nblocks = 1;                                     // block 0 unused: a descriptor is never 0
-  for (uint32_t i = 0; i < g->n; ++i) {
-    const uint32_t deg = indptr[i + 1] - indptr[i];
-    if (deg < bmin) continue;
-    uint32_t lg = 0;
-    while ((4ull << lg) < deg) ++lg;
-    if (nblocks + (1ull << lg) >= (1ull << 27)) break;               // descriptor range exhausted: no filter
-    desc[i] = (uint32_t)(nblocks << 5) | lg;
-    nblocks += 1ull << lg;
-    hubs.push_back(i);
-  }
-  if (hubs.empty()) return B2W_OK;
-  uint32_t* d_hubs = nullptr;
-  cudaError_t e = cudaMalloc(&g->bloom_desc, (size_t)g->n * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMalloc(&g->bloom_blocks, nblocks * sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMalloc(&d_hubs, hubs.size() * sizeof(uint32_t));
-  if (e == cudaSuccess) e = cudaMemcpy(g->bloom_desc, desc.data(), (size_t)g->n * sizeof(uint32_t), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(d_hubs, hubs.data(), hubs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemset(g->bloom_blocks, 0, nblocks * sizeof(unsigned long long));
-  if (e == cudaSuccess) {
-    const uint32_t nh = (uint32_t)hubs.size();
-    bloom_build_kernel<<<(nh * 32 + 255) / 256, 256>>>(d_hubs, nh, g->indptr, g->indices, g->bloom_desc, g->bloom_blocks);
-    e = cudaGetLastError();
-    if (e == cudaSuccess) e = cudaDeviceSynchronize();
-  }
-  if (d_hubs) cudaFree(d_hubs);
-  if (e != cudaSuccess) { bloom_free(g); return b2w_cuda_fail(e, "hub pre-filter build"); }
-  g->bloom_nblocks = nblocks;
-  return B2W_OK;
 }
 
 // Staging state of b2w_walk_host, cached in the handle so that repeated calls do not pay
@@ -245,8 +182,6 @@ extern "C" int b2w_graph_csr_create(int device, uint32_t n, uint64_t nnz, const 
   }
   g->max_degree = h.max_degree;
   if (!h.not_unweighted) g->flags |= B2W_GRAPH_UNWEIGHTED;
-  rc = bloom_build(g);
-  if (rc) { b2w_host_pipe_destroy(g->pipe); delete g; return rc; }
   *out = g;
   return B2W_OK;
 }
@@ -284,7 +219,6 @@ extern "C" int b2w_graph_info_get(const b2w_graph* g, b2w_graph_info* out) {
 extern "C" void b2w_graph_destroy(b2w_graph* g) {
   if (!g) return;
   cudaSetDevice(g->device);
-  bloom_free(g);
   b2w_host_pipe_destroy(g->pipe);
   delete g;
 }
@@ -364,7 +298,6 @@ extern "C" int b2w_walk(const b2w_graph* g, int mode, double p, double q, int ex
   P.n = g->n; P.indptr = g->indptr; P.indices = g->indices; P.data = g->data;
   P.dense = g->dense; P.nonzero = g->nonzero; P.thr = d_thr;
   P.alias_indptr = g->alias_indptr; P.alias_j = g->alias_j; P.alias_q = g->alias_q;
-  if (!(flags & B2W_FLAG_NO_HUB_FILTER)) { P.bloom_desc = g->bloom_desc; P.bloom_blocks = g->bloom_blocks; }
   P.start = d_start; P.feed = d_feed; P.out = d_out; P.ld_out = ld_out;
   P.row0 = row0; P.n_rows = n_rows; P.L = walk_length;
   P.key0 = (uint32_t)seed; P.key1 = (uint32_t)(seed >> 32);

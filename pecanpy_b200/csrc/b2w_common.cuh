@@ -27,12 +27,6 @@ struct b2w_graph {
   const uint64_t* alias_indptr;
   const uint32_t* alias_j;
   const float* alias_q;
-  // hub pre-filter (owned by the handle): a blocked Bloom filter per row of degree >= bloom_min; a few MB in
-  // total, L2 resident.  Lets the kernels discard most non-members of a hub row with ONE independent 8-byte
-  // load instead of a log2(deg)-deep chain of dependent probes.
-  uint32_t* bloom_desc;              // [n] 0 = none, else (first 64-bit block << 5) | log2(blocks)
-  unsigned long long* bloom_blocks;  // 64-bit blocks
-  uint64_t bloom_nblocks;
   // staging buffers / streams of b2w_walk_host (lazily allocated, guarded by their own mutex)
   b2w_host_pipe* pipe;
 };
@@ -49,8 +43,6 @@ struct WalkParams {
   const uint64_t* __restrict__ alias_indptr;
   const uint32_t* __restrict__ alias_j;
   const float* __restrict__ alias_q;
-  const uint32_t* __restrict__ bloom_desc;
-  const unsigned long long* __restrict__ bloom_blocks;
   const uint32_t* __restrict__ start;
   const double* __restrict__ feed;
   uint32_t* __restrict__ out;

@@ -71,36 +71,15 @@ __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__
 // Returns the number of common neighbours.  Rows of at most 32 entries return their single bitmap word in
 // `word0` (in_regs = true, nothing written to `bm`); otherwise the bitmap is in `bm` and the function ends with a
 // group sync so that it is visible to all lanes.
-// Blocked Bloom filter of one hub row (4 bits of one 64-bit block per element, ~16-32 bits per element).
-__host__ __device__ __forceinline__ uint32_t bloom_h1(uint32_t y) { return y * 0x9E3779B1u; }
-__host__ __device__ __forceinline__ unsigned long long bloom_mask(uint32_t y) {
-  const uint32_t h = (y ^ (y >> 15)) * 0x85EBCA77u;
-  return (1ull << (h & 63u)) | (1ull << ((h >> 6) & 63u)) | (1ull << ((h >> 12) & 63u)) | (1ull << ((h >> 18) & 63u));
-}
-__device__ __forceinline__ bool bloom_maybe(const unsigned long long* __restrict__ blocks, const uint32_t desc, const uint32_t y) {
-  const uint32_t lg = desc & 31u;
-  const uint32_t b = lg ? (bloom_h1(y) >> (32 - lg)) : 0u;
-  const unsigned long long blk = __ldg(blocks + (desc >> 5) + b);
-  const unsigned long long mk = bloom_mask(y);
-  return (blk & mk) == mk;
-}
-
-constexpr int B2W_CAND_CAP = 64;   // candidate key indices per group (shared memory)
-
 template <int G>
 __device__ __forceinline__ uint32_t membership_bitmap(const Tile<G>& T, const uint32_t* __restrict__ crow,
                                                       const uint32_t d, const uint32_t* __restrict__ prow,
                                                       const uint32_t pdeg, const uint32_t prev,
-                                                      uint32_t* __restrict__ bm, uint32_t& kp, uint32_t& word0, bool& in_regs,
-                                                      const unsigned long long* __restrict__ bloom_blocks,
-                                                      const uint32_t cbloom, uint32_t* __restrict__ cand) {
+                                                      uint32_t* __restrict__ bm, uint32_t& kp, uint32_t& word0, bool& in_regs) {
   const uint32_t nwords = (d + 31) >> 5;
   const uint32_t lgp = 32 - __clz(pdeg), lgd = 32 - __clz(d);
   const uint32_t fwd_cost = ((d + G - 1) / G) * (lgp + 2);
-  // with the hub pre-filter of row(cur) a reverse key costs ~3 instead of log2(deg) probes (survivors are compacted)
-  const uint32_t rev_cost = (cbloom != 0u && cand != nullptr)
-                                ? ((pdeg + G) / G) * 3 + 2 * (lgd + 2) + (nwords + G - 1) / G
-                                : ((pdeg + G) / G) * (lgd + 2) + (nwords + G - 1) / G;
+  const uint32_t rev_cost = ((pdeg + G) / G) * (lgd + 2) + (nwords + G - 1) / G;
   uint32_t m = 0;
   kp = B2W_NONE;
   // rows of cur that fit a few chunks always take the forward direction: the choice then does not depend on
@@ -142,43 +121,6 @@ __device__ __forceinline__ uint32_t membership_bitmap(const Tile<G>& T, const ui
       }
       m += __popc(bal);
     }
-  } else if (cbloom != 0u && cand != nullptr) {
-    // reverse with the hub pre-filter of row(cur): one independent 8-byte load per key discards (almost) all
-    // non-members; the survivors -- true common neighbours, prev itself, ~0.5 % false positives -- are
-    // compacted into `cand` and only they are bisected in row(cur).
-    for (uint32_t w = T.tl; w < nwords; w += G) bm[w] = 0u;
-    const uint32_t nkeys = pdeg + 1;
-    uint32_t mloc = 0, kploc = B2W_NONE, ncand = 0;
-    const uint32_t lt = (1u << T.tl) - 1u;
-    auto flush = [&]() {
-      T.sync();                                                      // candidates (and the zeroed bitmap) visible
-      for (uint32_t c0 = 0; c0 < ncand; c0 += G) {
-        const uint32_t ci = c0 + T.tl;
-        const bool valid = ci < ncand;
-        const uint32_t ii = valid ? cand[ci] : 0u;
-        const uint32_t y = valid ? (ii < pdeg ? __ldg(prow + ii) : prev) : B2W_NONE;
-        const uint32_t pos = lower_bound_u32(crow, d, y, lgd);
-        if (valid && pos < d && __ldg(crow + pos) == y) {
-          if (ii == pdeg) kploc = pos;
-          else if (y != prev) { atomicOr(&bm[pos >> 5], 1u << (pos & 31)); ++mloc; }
-        }
-      }
-      T.sync();                                                      // list may be overwritten
-      ncand = 0;
-    };
-    for (uint32_t c0 = 0; c0 < nkeys; c0 += G) {
-      const uint32_t ii = c0 + T.tl;
-      bool maybe = false;
-      if (ii < nkeys) maybe = (ii == pdeg) || bloom_maybe(bloom_blocks, cbloom, __ldg(prow + ii));
-      const uint32_t bal = T.ballot(maybe);
-      if (maybe) cand[ncand + __popc(bal & lt)] = ii;
-      ncand += __popc(bal);
-      if (ncand > (uint32_t)(B2W_CAND_CAP - G)) flush();
-    }
-    flush();
-    m = T.sum(mloc);
-    kp = T.minu(kploc);
-    return m;
   } else {
     for (uint32_t w = T.tl; w < nwords; w += G) bm[w] = 0u;
     T.sync();

@@ -132,14 +132,13 @@ __device__ __forceinline__ uint32_t uw_step(const Tile<G>& T, const WalkParams& 
                                             const uint32_t* __restrict__ crow, const uint32_t d,
                                             const uint32_t* __restrict__ prow, const uint32_t pdeg, const uint32_t prev,
                                             const bool has_prev, const double u, uint32_t* __restrict__ bm,
-                                            const uint32_t cbloom, uint32_t* __restrict__ cand,
                                             uint32_t& st_replays, uint32_t& st_overflow) {
   const double EC = 1.01 * 5.9604644775390625e-08;                    // 1.01 * 2^-24
   const uint32_t nwords = (d + 31) >> 5;
   // ---------------- phase 1: membership bitmap over the positions of row(cur)
   uint32_t m = 0, kp = NONE, word0 = 0;
   bool in_regs = false;
-  if (has_prev) m = membership_bitmap<G>(T, crow, d, prow, pdeg, prev, bm, kp, word0, in_regs, P.bloom_blocks, cbloom, cand);
+  if (has_prev) m = membership_bitmap<G>(T, crow, d, prow, pdeg, prev, bm, kp, word0, in_regs);
 
   // ---------------- phase 2: exact normaliser, three-valued probabilities
   const float w_o = has_prev ? C.w_out : 1.0f;                    // first step: every weight is 1
@@ -222,7 +221,6 @@ template <int G, int MINB>
 __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_kernel(const WalkParams P, const UwConsts C) {
   constexpr int GROUPS = UW_THREADS / G;
   __shared__ uint32_t s_bm[GROUPS][UW_BW];
-  __shared__ uint32_t s_cand[GROUPS][B2W_CAND_CAP];
   const Tile<G> T;
   const int gib = threadIdx.x / G;                                   // group in block
   const uint32_t ggid = blockIdx.x * GROUPS + gib;                    // global group id
@@ -241,7 +239,6 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_kernel(const WalkPar
     const uint32_t* prow = P.indices;
     uint32_t cs = __ldg(P.indptr + cur);
     uint32_t ce = __ldg(P.indptr + cur + 1);
-    uint32_t cbloom = P.bloom_desc ? __ldg(P.bloom_desc + cur) : 0u;
     uint32_t eff = L + 1;
     uint32_t myval = (T.tl == 0) ? cur : 0u;                          // lane (e mod G) holds output entry e
     double my_u = 0.0;
@@ -259,7 +256,7 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_kernel(const WalkPar
       uint32_t* const bm = (nwords <= UW_BW) ? s_bm[gib] : gbm;
       const uint32_t* const crow = P.indices + cs;
 
-      const uint32_t choice = uw_step<G>(T, P, C, crow, d, prow, pdeg, prev, has_prev, u, bm, cbloom, s_cand[gib], st_replays, st_overflow);
+      const uint32_t choice = uw_step<G>(T, P, C, crow, d, prow, pdeg, prev, has_prev, u, bm, st_replays, st_overflow);
 
       const uint32_t nxt = __ldg(crow + choice);                      // unchecked, as pecanpy.py:559
       if (T.tl == (j & (G - 1))) myval = nxt;
@@ -271,7 +268,6 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_kernel(const WalkPar
       cur = nxt;
       cs = __ldg(P.indptr + cur);
       ce = __ldg(P.indptr + cur + 1);
-      cbloom = P.bloom_desc ? __ldg(P.bloom_desc + cur) : 0u;
       ++st_steps;
     }
     // tail: the G-block holding entry j (first entry not produced), then zeros, then eff at L+1
@@ -383,12 +379,12 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_coop_kernel(const Wa
       uint32_t* const bmw = (((b_d + 31) >> 5) <= (uint32_t)UW_BW) ? s_wbm[wib] : gbm;
       uint32_t r2 = 0, o2 = 0;
       const uint32_t c = uw_step<32>(TW, P, C, P.indices + b_cs, b_d, reinterpret_cast<const uint32_t*>((uintptr_t)b_prow),
-                                     b_pdeg, b_prev, b_hp, b_u, bmw, 0u, nullptr, r2, o2);
+                                     b_pdeg, b_prev, b_hp, b_u, bmw, r2, o2);
       const uint32_t om = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << (src & ~(G - 1)));
       if (gmask == om) { choice = c; rep = r2; ovf = o2; }
       bigm &= ~om;
     }
-    if (active && !big) choice = uw_step<G>(T, P, C, crow, d, prow, pdeg, prev, has_prev, u, s_bm[gib], 0u, nullptr, rep, ovf);
+    if (active && !big) choice = uw_step<G>(T, P, C, crow, d, prow, pdeg, prev, has_prev, u, s_bm[gib], rep, ovf);
     if (active) {
       st_replays += rep; st_overflow += ovf;
       const uint32_t nxt = __ldg(crow + choice);                      // unchecked, as pecanpy.py:559

@@ -34,7 +34,6 @@ struct __align__(16) WarpBuf {
   float w[CAP];
   float ctot[CAP / 32];
   uint32_t bm[CAP / 32];
-  uint32_t cand[B2W_CAND_CAP];
 };
 
 struct WarpStats { uint32_t steps, replays, seqsums, overflow; };
@@ -60,7 +59,7 @@ __device__ __forceinline__ uint32_t otf_choice_warp(const WalkParams& P, const T
                                                     const uint32_t prev, const uint32_t ps, const uint32_t pdeg,
                                                     const double u, float* __restrict__ wbuf,
                                                     float* __restrict__ ctot, uint32_t* __restrict__ bm,
-                                                    uint32_t* __restrict__ cand, WarpStats& st) {
+                                                    WarpStats& st) {
   const int lane = T.lane;
   const uint32_t nchunks = (d + 31) >> 5;
   const uint32_t* const crow = P.indices + cs;
@@ -73,8 +72,7 @@ __device__ __forceinline__ uint32_t otf_choice_warp(const WalkParams& P, const T
   if (!EXTEND && has_prev) {
     uint32_t word0 = 0;
     bool in_regs = false;
-    membership_bitmap<32>(T, crow, d, prow, pdeg, prev, bm, kp, word0, in_regs, P.bloom_blocks,
-                          P.bloom_desc ? __ldg(P.bloom_desc + cur) : 0u, cand);
+    membership_bitmap<32>(T, crow, d, prow, pdeg, prev, bm, kp, word0, in_regs);
     if (in_regs) { if (lane == 0) bm[0] = word0; __syncwarp(); }
   }
 
@@ -247,7 +245,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) walk_sparse_warp_kernel
       const bool small = deg + 4 <= CAP;
       const uint32_t choice = otf_choice_warp<EXTEND>(P, T, cur, cs, deg, j > 1, prev, ps, pdeg, u,
                                                       small ? sbuf[wib].w : gw, small ? sbuf[wib].ctot : gctot,
-                                                      small ? sbuf[wib].bm : gbm, sbuf[wib].cand, st);
+                                                      small ? sbuf[wib].bm : gbm, st);
       const uint32_t nxt = __ldg(P.indices + cs + choice);            // unchecked, as pecanpy.py:559
       if (lane == (j & 31)) myval = nxt;
       if ((j & 31) == 31) {                                           // entries [j-31, j] complete: flush

@@ -243,24 +243,6 @@ def test_power_law_hubs_unweighted(mods, pq, flags):
     eng.close()
 
 
-@pytest.mark.parametrize("flags", [0, 1, 8, 9, 8 << 8, 16 << 8], ids=["auto", "auto-replay", "generic", "generic-replay", "uw-g8", "uw-g16"])
-@pytest.mark.parametrize("name", ["uhub400_sparseotf_n2v", "hub400_sparseotf_n2v", "dir150_sparseotf_deadends",
-                                  "w200_sparseotf_n2v"])
-def test_hub_prefilter_everywhere(mods, name, flags, monkeypatch):
-    """B2W_BLOOM_MIN=4 gives almost every row a Bloom pre-filter, so the filtered reverse search (candidate
-    compaction, list flushes, false positives, directed graphs, dead ends) runs on the small fixtures too."""
-    monkeypatch.setenv("B2W_BLOOM_MIN", "4")
-    c = load(name)
-    orc = mods["orc"]
-    L = int(c["walk_length"])
-    want = orc.walk_csr("SparseOTF", c["indptr"], c["indices"], c["data"], float(c["p"]), float(c["q"]), c["start"], L,
-                        rng=orc.RNG_PHILOX, seed=78)
-    eng = mods["WalkEngine"].from_csr(c["indptr"], c["indices"], c["data"])
-    got = to_np(eng.walk("SparseOTF", float(c["p"]), float(c["q"]), c["start"], L, seed=78, flags=flags))
-    assert np.array_equal(got, want), first_diff(got, want)
-    eng.close()
-
-
 def test_power_law_hubs_weighted(mods):
     from pecanpy_b200.synth import power_law_csr
     orc = mods["orc"]
