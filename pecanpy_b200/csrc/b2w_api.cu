@@ -253,7 +253,8 @@ extern "C" size_t b2w_walk_work_bytes(const b2w_graph* g, int mode) {
     size_t a = b2w_sparse_warp_work_bytes(g), b = b2w_uw_work_bytes(g);
     return a > b ? a : b;
   }
-  return 256;   // every other kernel: the row-queue counter
+  if (mode == B2W_MODE_DENSE_OTF) return 256;
+  return 0;
 }
 
 extern "C" int b2w_walk(const b2w_graph* g, int mode, double p, double q, int extend, const float* d_thr,
@@ -287,7 +288,7 @@ extern "C" int b2w_walk(const b2w_graph* g, int mode, double p, double q, int ex
     return B2W_ERR_INVALID;
   }
   const bool warp_kernel = mode == B2W_MODE_SPARSE_OTF && !(flags & B2W_FLAG_THREAD_PER_WALKER);
-  size_t need = (warp_kernel || dense) ? b2w_walk_work_bytes(g, mode) : 256;
+  size_t need = (warp_kernel || dense) ? b2w_walk_work_bytes(g, mode) : 0;
   if (need && (!d_work || work_bytes < need)) {
     b2w_set_error("b2w_walk: scratch too small (%zu < %zu bytes)", work_bytes, need);
     return B2W_ERR_INVALID;

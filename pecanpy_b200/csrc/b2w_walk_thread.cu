@@ -23,16 +23,8 @@ template <int MODE, bool EXTEND>
 __global__ void __launch_bounds__(256) walk_thread_kernel(const WalkParams P) {
   const uint32_t L = P.L;
   uint64_t steps = 0, overflow = 0;
-  // persistent grid, dynamic row queue: each warp claims 32 consecutive rows at a time (no wave
-  // quantisation, and the 32 output rows of a warp are adjacent in memory)
-  const int lane = threadIdx.x & 31;
-  for (;;) {
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(P.counter, 32ull);
-    base = __shfl_sync(B2W_FULL, base, 0);
-    if (base >= P.n_rows) break;
-    const uint64_t i = base + lane;
-    if (i >= P.n_rows) continue;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < P.n_rows;
+       i += (uint64_t)gridDim.x * blockDim.x) {
     uint32_t* out = P.out + i * P.ld_out;
     const uint64_t row = P.row0 + i;
     uint32_t cur = P.start[i];
@@ -97,18 +89,12 @@ __global__ void __launch_bounds__(256) walk_thread_kernel(const WalkParams P) {
 
 template <int MODE, bool EXTEND>
 int launch(const b2w_graph* g, const WalkParams& P, cudaStream_t s) {
-  const int threads = 256;
-  WalkParams Q = P;
-  Q.counter = reinterpret_cast<unsigned long long*>(P.work);
-  B2W_CUDA(cudaMemsetAsync(Q.counter, 0, 8, s));
-  int per_sm = 0;
-  B2W_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, walk_thread_kernel<MODE, EXTEND>, threads, 0));
-  if (per_sm < 1) per_sm = 1;
+  int threads = 256;
   uint64_t want = (P.n_rows + threads - 1) / threads;
-  uint64_t cap = (uint64_t)g->num_sms * per_sm;
+  uint64_t cap = (uint64_t)g->num_sms * 8 * 4;   // grid-stride beyond a few waves
   int blocks = (int)(want < cap ? want : cap);
   if (blocks < 1) blocks = 1;
-  walk_thread_kernel<MODE, EXTEND><<<blocks, threads, 0, s>>>(Q);
+  walk_thread_kernel<MODE, EXTEND><<<blocks, threads, 0, s>>>(P);
   return b2w_cuda_fail(cudaGetLastError(), "walk_thread_kernel launch");
 }
 

@@ -28,9 +28,6 @@
 namespace {
 
 constexpr int WARPS_PER_CTA = 8;
-#ifndef B2W_WARP_MINB
-#define B2W_WARP_MINB 4
-#endif
 constexpr int CAP = 1024;   // staged weights per warp in shared memory (longer rows use global scratch)
 
 struct __align__(16) WarpBuf {
@@ -208,7 +205,7 @@ __device__ __forceinline__ uint32_t otf_choice_warp(const WalkParams& P, const T
 }
 
 template <bool EXTEND>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, B2W_WARP_MINB) walk_sparse_warp_kernel(const WalkParams P) {
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) walk_sparse_warp_kernel(const WalkParams P) {
   __shared__ WarpBuf sbuf[WARPS_PER_CTA];
   const Tile<32> T;
   const int lane = threadIdx.x & 31;
