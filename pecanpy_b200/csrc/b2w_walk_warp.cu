@@ -11,13 +11,14 @@
 //           the cheaper side (b2w_membership.cuh); (node2vec+) per-element lower_bound in row(prev),
 //           because each common neighbour also needs w(prev, x) / thr[x].
 //  phase 2  stream the weights of row(cur) once (coalesced), form the biased weights w_k, stage them
-//           in shared memory (rows above 1020 entries: a per-warp scratch row that stays in L2) and
-//           keep one f32 partial sum per 32-element chunk.
+//           in shared memory (rows above 1020 entries: a per-warp scratch row that stays in L2); then every
+//           lane sums one contiguous segment of the staged row (odd pitch: bank-conflict free) and a single
+//           warp scan yields the segment prefixes.
 //  filter   Let P_k be the exact prefix sums of w.  The reference computes S = fl-sum(w) (relative error
 //           gamma_{d-1}), probs_k = fl(w_k / S) (2^-24 each) and cdf_k = fl-cumsum (gamma_k); all terms are
 //           non-negative, so cdf_k = (P_k / P_{d-1}) (1 +- (gamma_k + gamma_{d-1} + 2^-24)).  The warp's own
-//           chunk totals / scans are float summations of the same terms with depth <= nchunks + 12.
-//           Hence |cdf_k - A_k / T| <= e_k A_k / T with e_k = (k + d + 2 nchunks + 40) 1.01 2^-24, and the
+//           segment sums / scans are float summations of the same terms with depth <= mseg + 16 (mseg =
+//           elements per lane).  Hence |cdf_k - A_k / T| <= e_k A_k / T with e_k = (k + d + 2 mseg + 48) 1.01 2^-24, and the
 //           first k with A_k (1 + e_k) >= u T is the reference's choice whenever A_k (1 - e_k) >= u T.
 //  replay   otherwise (probability ~ d^2 1e-7 per step) the warp re-runs the reference's recurrences
 //           exactly: sequential f32 sum, fdiv per element, sequential f32 cumsum (float4 broadcast reads).
@@ -32,7 +33,6 @@ constexpr int CAP = 1024;   // staged weights per warp in shared memory (longer 
 
 struct __align__(16) WarpBuf {
   float w[CAP];
-  float ctot[CAP / 32];
   uint32_t bm[CAP / 32];
 };
 
@@ -58,7 +58,7 @@ __device__ __forceinline__ uint32_t otf_choice_warp(const WalkParams& P, const T
                                                     const uint32_t cs, const uint32_t d, const bool has_prev,
                                                     const uint32_t prev, const uint32_t ps, const uint32_t pdeg,
                                                     const double u, float* __restrict__ wbuf,
-                                                    float* __restrict__ ctot, uint32_t* __restrict__ bm,
+                                                    uint32_t* __restrict__ bm,
                                                     WarpStats& st) {
   const int lane = T.lane;
   const uint32_t nchunks = (d + 31) >> 5;
@@ -211,10 +211,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) walk_sparse_warp_kernel
   const int lane = threadIdx.x & 31;
   const int wib = threadIdx.x >> 5;
   const uint32_t warp_gid = blockIdx.x * WARPS_PER_CTA + wib;
-  // global scratch row of this warp: [w: work_stride floats][ctot: work_stride/32][bitmap: work_stride/32]
-  float* const gw = P.work + (size_t)warp_gid * (P.work_stride + 2 * (P.work_stride / 32));
-  float* const gctot = gw + P.work_stride;
-  uint32_t* const gbm = reinterpret_cast<uint32_t*>(gctot + P.work_stride / 32);
+  // global scratch row of this warp: [w: work_stride floats][bitmap: work_stride/32 words]
+  float* const gw = P.work + (size_t)warp_gid * (P.work_stride + P.work_stride / 32);
+  uint32_t* const gbm = reinterpret_cast<uint32_t*>(gw + P.work_stride);
   const uint32_t L = P.L;
   WarpStats st = {0, 0, 0, 0};
 
@@ -244,7 +243,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) walk_sparse_warp_kernel
       const double u = __shfl_sync(B2W_FULL, my_u, (j - 1) & 31);
       const bool small = deg + 4 <= CAP;
       const uint32_t choice = otf_choice_warp<EXTEND>(P, T, cur, cs, deg, j > 1, prev, ps, pdeg, u,
-                                                      small ? sbuf[wib].w : gw, small ? sbuf[wib].ctot : gctot,
+                                                      small ? sbuf[wib].w : gw,
                                                       small ? sbuf[wib].bm : gbm, st);
       const uint32_t nxt = __ldg(P.indices + cs + choice);            // unchecked, as pecanpy.py:559
       if (lane == (j & 31)) myval = nxt;
@@ -295,7 +294,7 @@ uint32_t b2w_sparse_warp_total_warps(const b2w_graph* g) {
 size_t b2w_sparse_warp_work_bytes(const b2w_graph* g) {
   // [0,256): row-queue counter; then one scratch row per resident warp for degrees above CAP-4
   size_t stride = (g->max_degree + 4 > (uint32_t)CAP) ? (((size_t)g->max_degree + 4 + 127) & ~(size_t)127) : 0;
-  return 256 + (size_t)b2w_sparse_warp_total_warps(g) * (stride + 2 * (stride / 32)) * sizeof(float);
+  return 256 + (size_t)b2w_sparse_warp_total_warps(g) * (stride + stride / 32) * sizeof(float);
 }
 
 int b2w_launch_sparse_warp(const b2w_graph* g, const WalkParams& P_in, cudaStream_t s) {
