@@ -57,39 +57,57 @@ class BaseGraph:
 
 
 def _read_edge_list(path: str, weighted: bool, directed: bool, delimiter: str = "\t"):
-    """Parse an ``.edg`` file into (ids, rows, cols, weights) with the reference's conventions:
-    first-seen node order, non-positive weights dropped with a warning, later duplicates win."""
-    ids: Dict[str, int] = {}
-    edges: Dict[tuple, float] = {}
+    """Parse an ``.edg`` file into (ids, rows, cols, weights) with the reference's conventions
+    (graph.py:160-305): node order = first appearance (id1 then id2, line by line), non-positive weights
+    dropped with a warning, a later definition of the same edge overwrites an earlier one.
+
+    Vectorised (one NumPy pass instead of a Python loop per edge) so that 10^7-edge files load in seconds."""
     with open(path, encoding="utf-8") as f:
-        for line in f:
-            terms = line.strip().split(delimiter)
-            a, b = terms[0].strip(), terms[1].strip()
-            w = 1.0
-            if weighted:
-                if len(terms) != 3:
-                    raise ValueError(f"Expecting three columns in the edge list file for a weighted graph, "
-                                     f"got {len(terms)} instead: {line!r}")
-                w = float(terms[-1])
-            if w <= 0:
-                warnings.warn(f"Non-positive edge ignored: w({a},{b}) = {w}", RuntimeWarning, stacklevel=2)
-                continue
-            ia = ids.setdefault(a, len(ids))
-            ib = ids.setdefault(b, len(ids))
-            edges[(ia, ib)] = w
-            if not directed:
-                edges[(ib, ia)] = w
-    names = [None] * len(ids)
-    for k, v in ids.items():
-        names[v] = k
-    if edges:
-        rc = np.array(list(edges.keys()), dtype=np.int64)
-        w = np.array(list(edges.values()), dtype=np.float64)
-        rows, cols = rc[:, 0], rc[:, 1]
+        lines = f.read().splitlines()
+    lines = [ln for ln in lines if ln.strip()]
+    if not lines:
+        return [], np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.float64)
+    parts = [ln.strip().split(delimiter) for ln in lines]
+    if weighted:
+        for ln, t in zip(lines, parts):
+            if len(t) != 3:
+                raise ValueError(f"Expecting three columns in the edge list file for a weighted graph, "
+                                 f"got {len(t)} instead: {ln!r}")
+        w = np.array([float(t[-1]) for t in parts], dtype=np.float64)
     else:
-        rows = cols = np.zeros(0, dtype=np.int64)
-        w = np.zeros(0, dtype=np.float64)
-    return names, rows, cols, w
+        w = np.ones(len(parts), dtype=np.float64)
+    a = np.array([t[0].strip() for t in parts], dtype=object)
+    b = np.array([t[1].strip() for t in parts], dtype=object)
+    bad = w <= 0
+    if bad.any():
+        for i in np.flatnonzero(bad)[:20]:
+            warnings.warn(f"Non-positive edge ignored: w({a[i]},{b[i]}) = {w[i]}", RuntimeWarning, stacklevel=2)
+        a, b, w = a[~bad], b[~bad], w[~bad]
+    # first-appearance order over the interleaved sequence a0, b0, a1, b1, ...
+    inter = np.empty(2 * a.size, dtype=object)
+    inter[0::2], inter[1::2] = a, b
+    uniq, first, inv = np.unique(inter, return_index=True, return_inverse=True)
+    rank = np.empty(uniq.size, dtype=np.int64)
+    rank[np.argsort(first, kind="stable")] = np.arange(uniq.size)
+    names = [None] * uniq.size
+    for u, r in zip(uniq, rank):
+        names[r] = u
+    ia, ib = rank[inv[0::2]], rank[inv[1::2]]
+    seq = np.arange(ia.size, dtype=np.int64)
+    if directed:
+        rows, cols, ww, order = ia, ib, w, seq
+    else:
+        rows = np.concatenate([ia, ib]); cols = np.concatenate([ib, ia])
+        ww = np.concatenate([w, w]); order = np.concatenate([seq, seq])
+    # later definitions win: keep the last occurrence of every (row, col)
+    n = max(len(names), 1)
+    key = rows * n + cols
+    srt = np.lexsort((order, key))
+    key_s = key[srt]
+    last = np.ones(key_s.size, dtype=bool)
+    last[:-1] = key_s[1:] != key_s[:-1]
+    keep = srt[last]
+    return names, rows[keep], cols[keep], ww[keep]
 
 
 def _coo_to_csr(n: int, rows, cols, w):
