@@ -39,3 +39,18 @@ def sharded_walks(walk_block: Callable[[int, int, torch.Tensor], None], total_ro
     if world > 1:
         dist.all_gather_into_tensor(full.view(-1), mine.reshape(-1), group=group)
     return full[:total_rows]
+
+
+def simulate_walks_distributed(engine, mode, p: float, q: float, start, walk_length: int, seed: int, *,
+                               extend: bool = False, flags: int = 0, group=None) -> torch.Tensor:
+    """All-rank walk of the (identical, host-shuffled) ``start`` array: every rank holds a replica of the graph
+    in ``engine`` (a :class:`pecanpy_b200.engine.WalkEngine` on its own GPU), walks its row block and receives
+    the full ``int32[len(start), walk_length + 2]`` matrix (bit-identical for any number of ranks)."""
+    import numpy as np
+    start = np.ascontiguousarray(start, dtype=np.uint32)
+
+    def walk_block(lo: int, hi: int, out_block: torch.Tensor) -> None:
+        engine.walk(mode, p, q, start[lo:hi], walk_length, seed=seed, extend=extend, row0=lo, out=out_block,
+                    flags=flags, collect_stats=False)
+
+    return sharded_walks(walk_block, start.size, walk_length + 2, engine.device, group=group)
