@@ -302,8 +302,11 @@ def main():
         eng = WalkEngine.from_csr(g["indptr"], g["indices"], g["data"], device=dev)
     extras = {}
     if wl["extend"]:
-        prep_reference_extras(wl, g)
-        eng.set_thresholds(g["thr"])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        eng.compute_thresholds(wl.get("gamma", 0.0))      # b2w_noise_thresholds (device), not the oracle
+        torch.cuda.synchronize()
+        extras["thresholds_ms"] = 1e3 * (time.perf_counter() - t0)
     if wl["mode"] == "PreComp":
         torch.cuda.synchronize()
         t0 = time.perf_counter()

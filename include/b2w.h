@@ -117,6 +117,15 @@ int b2w_graph_dense_create(int device, uint32_t num_nodes, const double* d_data,
 int b2w_graph_info_get(const b2w_graph* g, b2w_graph_info* out);
 void b2w_graph_destroy(b2w_graph* g);
 
+/* ---- node2vec+ noise thresholds ----------------------------------------------------------
+ * Replaces SparseRWGraph.get_noise_thresholds (rw/sparse_rw.py:22-35) and
+ * DenseRWGraph.get_noise_thresholds (rw/dense_rw.py:11-19), Python loops over the nodes there:
+ *     d_thr[i] = max(mean(w_i) + gamma * std(w_i), 0),   w_i = stored weights of row i   (f32[n])
+ * with NumPy's own arithmetic: pairwise summation, float32 for CSR rows, float64 for dense rows
+ * (rounded to float32 on the store), NaN for a row without stored weights.  Bit-identical to NumPy >= 2
+ * for a Python-float gamma (the scalar is "weak": the CSR expression stays in float32). */
+int b2w_noise_thresholds(const b2w_graph* g, double gamma, float* d_thr, void* stream);
+
 /* ---- PreComp alias tables --------------------------------------------------------------
  * Replaces PreComp.preprocess_transition_probs (pecanpy.py:442-507) + alias_setup
  * (pecanpy.py:617-665).  The caller computes alias_indptr = [0, cumsum(deg^2)] as u64[n+1]

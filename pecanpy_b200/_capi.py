@@ -31,7 +31,7 @@ EXPORTS = [
     "b2w_version", "b2w_last_error", "b2w_device_count", "b2w_graph_csr_create", "b2w_graph_dense_create",
     "b2w_graph_info_get", "b2w_graph_destroy", "b2w_alias_build_work_bytes", "b2w_alias_build",
     "b2w_alias_build_first_order", "b2w_graph_set_alias", "b2w_walk_work_bytes", "b2w_walk", "b2w_walk_host",
-    "b2w_count_steps", "b2w_philox_selftest", "b2w_walk_kernel_name",
+    "b2w_count_steps", "b2w_philox_selftest", "b2w_walk_kernel_name", "b2w_noise_thresholds",
 ]
 
 
@@ -81,6 +81,7 @@ def lib():
     L.b2w_walk_host.argtypes = [vp, i32, dbl, dbl, i32, vp, vp, u64, u64, u32, u64, vp, u64, C.POINTER(WalkStats), u32]
     L.b2w_walk_kernel_name.argtypes = [vp, i32, dbl, dbl, i32, u32]
     L.b2w_walk_kernel_name.restype = C.c_char_p
+    L.b2w_noise_thresholds.argtypes = [vp, dbl, vp, vp]
     L.b2w_count_steps.argtypes = [vp, u64, u32, u64, vp, vp]
     L.b2w_philox_selftest.argtypes = [C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
     for name in EXPORTS:

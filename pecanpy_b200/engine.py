@@ -119,8 +119,20 @@ class WalkEngine:
         return gi
 
     def set_thresholds(self, thr: Optional[np.ndarray]):
-        """node2vec+ noise thresholds (float32[n], computed on the host as in the reference)."""
+        """Attach caller-computed node2vec+ noise thresholds (float32[n]); see compute_thresholds()."""
         self.thr = None if thr is None else _to_dev(np.ascontiguousarray(thr, dtype=np.float32), self.device)
+
+    def compute_thresholds(self, gamma: float) -> torch.Tensor:
+        """node2vec+ noise thresholds on the GPU (b2w_noise_thresholds), bit-identical to the reference's NumPy
+        loop (rw/sparse_rw.py:22-35, rw/dense_rw.py:11-19); the result is attached to the engine and returned
+        (float32[n], device)."""
+        with torch.cuda.device(self.device):
+            thr = torch.empty(self.n, dtype=torch.float32, device=self.device)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            capi.check(self.lib.b2w_noise_thresholds(self.handle, float(gamma), _ptr(thr), C.c_void_p(stream)),
+                       "b2w_noise_thresholds")
+        self.thr = thr
+        return thr
 
     def _scratch(self, key: str, nbytes: int) -> Optional[torch.Tensor]:
         if nbytes == 0:

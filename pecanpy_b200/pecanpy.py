@@ -53,8 +53,15 @@ class Base(BaseGraph):
         if self._engine is None:
             self._engine = self._make_engine()
             if self.extend and self._MODE in ("SparseOTF", "DenseOTF", "PreComp"):
-                self._engine.set_thresholds(self.get_noise_thresholds())
+                self._engine.compute_thresholds(self.gamma)
         return self._engine
+
+    def get_noise_thresholds(self) -> np.ndarray:
+        """``max(mean + gamma * std, 0)`` of every row's weights (rw/sparse_rw.py:22-35, rw/dense_rw.py:11-19),
+        computed by the device kernel (bit-identical to the reference's NumPy loop) and returned as float32[n]."""
+        eng = self.engine
+        thr = eng.thr if (self.extend and eng.thr is not None) else eng.compute_thresholds(self.gamma)
+        return thr.cpu().numpy()
 
     def release(self):
         if self._engine is not None:
@@ -125,17 +132,6 @@ class _SparseBase(Base, SparseGraph):
         from .engine import WalkEngine
         return WalkEngine.from_csr(self.indptr, self.indices, self.data, device=self.device)
 
-    def get_noise_thresholds(self) -> np.ndarray:
-        """mean + gamma * std of each row's weights, clipped at 0 (rw/sparse_rw.py:22-35; host NumPy,
-        as in the reference -- its pairwise f32 reductions are part of the bit-exact contract)."""
-        thr = np.zeros(self.num_nodes, dtype=np.float32)
-        data, indptr = self.data, self.indptr
-        with np.errstate(all="ignore"):
-            for i in range(self.num_nodes):
-                row = data[indptr[i]:indptr[i + 1]]
-                thr[i] = row.mean() + self.gamma * row.std()
-        return np.maximum(thr, 0)
-
 
 class SparseOTF(_SparseBase):
     """Sparse graph, transition probabilities on the fly (reference pecanpy.py:510-561)."""
@@ -198,12 +194,3 @@ class DenseOTF(Base, DenseGraph):
     def _make_engine(self):
         from .engine import WalkEngine
         return WalkEngine.from_dense(self.data, self.nonzero, device=self.device)
-
-    def get_noise_thresholds(self) -> np.ndarray:
-        """rw/dense_rw.py:11-19 (host NumPy, as in the reference)."""
-        thr = np.zeros(self.num_nodes, dtype=np.float32)
-        with np.errstate(all="ignore"):
-            for i in range(self.num_nodes):
-                w = self.data[i, self.nonzero[i]]
-                thr[i] = w.mean() + self.gamma * w.std()
-        return np.maximum(thr, 0)

@@ -332,3 +332,77 @@ def test_drop_in_classes_match_oracle(mods):
                                 rng=orc.RNG_PHILOX, seed=0)
         assert walks == [[IDS[i] for i in row[: row[-1]]] for row in want], name
         g.release()
+
+
+# ---------------------------------------------------------------------------------------------- thresholds
+def _same_f32(a, b):
+    nan = np.isnan(a)
+    return np.array_equal(nan, np.isnan(b)) and np.array_equal(a[~nan].view(np.uint32), b[~nan].view(np.uint32))
+
+
+THR_FIXTURES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz"))
+                      if "_ext" in os.path.basename(f))
+
+
+@pytest.mark.parametrize("name", THR_FIXTURES)
+def test_noise_thresholds_equal_reference_fixture(mods, name):
+    """b2w_noise_thresholds vs the `thr` array the unmodified reference computed (get_noise_thresholds)."""
+    c = load(name)
+    gamma = float(c["gamma"]) if "gamma" in c else 0.0
+    if "dense" in c:
+        eng = mods["WalkEngine"].from_dense(c["dense"], c["nonzero"])
+    else:
+        eng = mods["WalkEngine"].from_csr(c["indptr"], c["indices"], c["data"])
+    got = eng.compute_thresholds(gamma).cpu().numpy()
+    assert _same_f32(got, c["thr"].astype(np.float32))
+    eng.close()
+
+
+@pytest.mark.parametrize("gamma", [0.0, 0.25, -0.7, 3.3])
+def test_noise_thresholds_csr_vs_numpy(mods, gamma):
+    """Rows of every length class of NumPy's pairwise summation (< 8, <= 128, recursive), empty rows, a hub."""
+    rng = np.random.default_rng(5)
+    n = 6000
+    deg = np.concatenate([rng.integers(0, 40, n - 60), rng.integers(100, 700, 50), [0, 1, 7, 8, 9, 127, 128, 129, 5000, 3]])
+    # any sorted duplicate-free rows will do: the thresholds only read the weights
+    indptr = np.zeros(n + 1, dtype=np.uint32)
+    np.cumsum(deg, out=indptr[1:])
+    indices = np.concatenate([np.sort(rng.choice(n, int(d), replace=False)) for d in deg]).astype(np.uint32)
+    data = (np.float32(0.01) + np.float32(0.99) * rng.random(indices.size, dtype=np.float32)).astype(np.float32)
+    eng = mods["WalkEngine"].from_csr(indptr, indices, data)
+    got = eng.compute_thresholds(gamma).cpu().numpy()
+    want = mods["orc"].noise_thresholds_csr(indptr, data, gamma)
+    assert _same_f32(got, want)
+    eng.close()
+
+
+@pytest.mark.parametrize("n", [333, 1024])
+@pytest.mark.parametrize("gamma", [0.0, 0.5, -2.0])
+def test_noise_thresholds_dense_vs_numpy(mods, n, gamma):
+    rng = np.random.default_rng(6)
+    nz = rng.random((n, n)) < 0.4
+    nz[3] = False
+    nz[4] = False; nz[4, 10] = True
+    nz[5] = True
+    data = np.where(nz, 0.01 + 0.99 * rng.random((n, n)), 0.0)
+    eng = mods["WalkEngine"].from_dense(data, nz)
+    got = eng.compute_thresholds(gamma).cpu().numpy()
+    want = mods["orc"].noise_thresholds_dense(data, nz, gamma)
+    assert _same_f32(got, want)
+    eng.close()
+
+
+def test_dropin_extend_uses_device_thresholds(mods):
+    """SparseOTF(extend=True): thresholds come from the GPU kernel and the walks equal the oracle's."""
+    from pecanpy_b200 import pecanpy as node2vec
+    c = load("w200_sparseotf_ext_g05")
+    g = node2vec.SparseOTF(p=float(c["p"]), q=float(c["q"]), extend=True, gamma=float(c["gamma"]), random_state=11)
+    g.indptr, g.indices, g.data = c["indptr"], c["indices"], c["data"]
+    g.set_node_ids(None, implicit_ids=True, num_nodes=c["indptr"].size - 1)
+    thr = g.get_noise_thresholds()
+    assert _same_f32(thr, c["thr"].astype(np.float32))
+    mat = g.simulate_walks_array(2, 15)
+    start = mods["orc"].shuffled_start(g.num_nodes, 2, 11)
+    want = mods["orc"].walk_csr("SparseOTF", c["indptr"], c["indices"], c["data"], float(c["p"]), float(c["q"]), start, 15,
+                                extend=True, thr=c["thr"], rng=mods["orc"].RNG_PHILOX, seed=11)
+    assert np.array_equal(mat, want), first_diff(mat, want)
