@@ -40,7 +40,29 @@ def _deps_mtime() -> float:
     return max(m, os.path.getmtime(os.path.abspath(__file__)))
 
 
+def pylists_path() -> str:
+    import sysconfig
+    return os.path.join(LIB_DIR, "_b2w_pylists" + (sysconfig.get_config_var("EXT_SUFFIX") or ".so"))
+
+
+def build_pylists(force: bool = False) -> str:
+    """The CPython extension that turns a walk matrix into List[List[str]] (csrc/b2w_pylists.c), with gcc."""
+    import sysconfig
+    src, out = os.path.join(CSRC, "b2w_pylists.c"), pylists_path()
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= os.path.getmtime(src):
+        return out
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = ["gcc", "-O2", "-fPIC", "-shared", "-std=c11", "-Wall", "-I", sysconfig.get_paths()["include"], src, "-o",
+           out + ".tmp"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"gcc failed for b2w_pylists.c:\n{r.stdout}\n{r.stderr}")
+    os.replace(out + ".tmp", out)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    build_pylists(force)
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime():
         return LIB
     os.makedirs(OBJ_DIR, exist_ok=True)

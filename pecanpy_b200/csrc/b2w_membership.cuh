@@ -44,20 +44,66 @@ struct Tile {
   }
 };
 
-// Number of elements of the sorted row[0..n) that are < x.  Branch-free, `lg` = 32 - clz(n)
-// iterations (uniform across the group): pos only grows over a prefix of elements < x.
-__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__ row, uint32_t n, uint32_t x,
-                                                    uint32_t lg) {
-  const uint32_t* const rowm1 = row - 1;
-  uint32_t pos = 0;
-  for (uint32_t step = lg ? (1u << (lg - 1)) : 0u; step; step >>= 1) {
-    const uint32_t idx = pos | step;                                  // pos has no bit at or below `step`
-    uint32_t v = 0xFFFFFFFFu;
-    if (idx <= n) v = __ldg(rowm1 + idx);
-    if (v < x) pos = idx;
+// Number of elements of the sorted, duplicate-free row[0..n) (n >= 1) that are < x, and whether x is one
+// of them.  `k` = floor(log2 n) must be uniform across the group.  k + 1 dependent loads, none of them out
+// of bounds, no data-dependent branch and (fully unrolled through a jump on k) five instructions per probe:
+// address, load, compare, predicated add, predicated move.
+//   * first probe at row[2^k - 1] picks one of two overlapping windows of 2^k possible answers:
+//     [0, 2^k - 1] or [n - 2^k + 1, n]  (the second contains the impossible answers below 2^k, harmless);
+//   * invariant: answer in [lo, lo + 2S - 1] with lo + 2S - 1 <= n; probe row[lo + S - 1] (always < n);
+//   * x is in the row iff the LAST probe that loaded a value >= x loaded x itself: telling answer a from a + 1
+//     needs exactly the probe of row[a] (the top of the first window, row[2^k - 1], is the first probe), probes
+//     with v >= x move down the row, and below row[a] every value is < x.
+// (The first version of this search, `if (idx <= n) v = row[idx - 1]` inside a counted loop, compiled to a
+// real branch with a reconvergence barrier: 13 instructions per probe, a third of the whole kernel --
+// profiles/r1_uw_g32_powerlaw_nw1_src.txt.)
+#define B2W_LB_PROBE(S)                              \
+  {                                                  \
+    const uint32_t v_ = __ldg(row + lo + ((S) - 1)); \
+    if (v_ < x) lo += (S); else ge = v_;             \
   }
-  return pos;
+// WARP_UNIFORM (k is the same for all 32 lanes, i.e. 32-lane groups): jump into the unrolled probe sequence.
+// Sub-warp groups have different k per group; jumping to different entry points would serialise the groups
+// of a warp, so they run a counted loop instead (lanes that finish early wait at the loop exit).
+template <bool WARP_UNIFORM>
+__device__ __forceinline__ uint32_t lower_bound_eq(const uint32_t* __restrict__ row, const uint32_t n, const uint32_t x,
+                                                   const uint32_t k, bool& found) {
+  const uint32_t top = 1u << k;
+  const uint32_t v0 = __ldg(row + (top - 1));
+  uint32_t ge = (v0 < x) ? B2W_NONE : v0;                            // value of the last probe that was >= x
+  uint32_t lo = (v0 < x) ? n - top + 1 : 0u;
+  if (WARP_UNIFORM) {
+    uint32_t kk = k;
+    for (; kk > 16; --kk) B2W_LB_PROBE(1u << (kk - 1))                // rows beyond 2^17 entries
+    switch (kk) {
+      case 16: B2W_LB_PROBE(32768u)
+      case 15: B2W_LB_PROBE(16384u)
+      case 14: B2W_LB_PROBE(8192u)
+      case 13: B2W_LB_PROBE(4096u)
+      case 12: B2W_LB_PROBE(2048u)
+      case 11: B2W_LB_PROBE(1024u)
+      case 10: B2W_LB_PROBE(512u)
+      case 9: B2W_LB_PROBE(256u)
+      case 8: B2W_LB_PROBE(128u)
+      case 7: B2W_LB_PROBE(64u)
+      case 6: B2W_LB_PROBE(32u)
+      case 5: B2W_LB_PROBE(16u)
+      case 4: B2W_LB_PROBE(8u)
+      case 3: B2W_LB_PROBE(4u)
+      case 2: B2W_LB_PROBE(2u)
+      case 1: B2W_LB_PROBE(1u)
+      default: break;
+    }
+  } else {
+    for (uint32_t S = top >> 1; S; S >>= 1) {
+      const uint32_t v_ = __ldg(row + (lo + S - 1u));                 // 32-bit index first: one IMAD.WIDE
+      if (v_ < x) lo += S; else ge = v_;
+    }
+  }
+  found = ge == x;                                                   // (x == B2W_NONE: callers mask invalid lanes)
+  return lo;
 }
+#undef B2W_LB_PROBE
 
 
 // Membership of the neighbours of `cur` in N(prev) as a BITMAP over the positions of row(cur)
@@ -77,7 +123,8 @@ __device__ __forceinline__ uint32_t membership_bitmap(const Tile<G>& T, const ui
                                                       const uint32_t pdeg, const uint32_t prev,
                                                       uint32_t* __restrict__ bm, uint32_t& kp, uint32_t& word0, bool& in_regs) {
   const uint32_t nwords = (d + 31) >> 5;
-  const uint32_t lgp = 32 - __clz(pdeg), lgd = 32 - __clz(d);
+  const uint32_t lgp = 32 - __clz(pdeg), lgd = 32 - __clz(d);          // probes per search (cost model)
+  const uint32_t kp2 = 31 - __clz(pdeg), kd2 = 31 - __clz(d);          // floor(log2): pdeg >= 1, d >= 1
   const uint32_t fwd_cost = ((d + G - 1) / G) * (lgp + 2);
   const uint32_t rev_cost = ((pdeg + G) / G) * (lgd + 2) + (nwords + G - 1) / G;
   uint32_t m = 0;
@@ -93,8 +140,8 @@ __device__ __forceinline__ uint32_t membership_bitmap(const Tile<G>& T, const ui
       const uint32_t k = c0 + T.tl;
       const bool valid = k < d;
       const uint32_t x = valid ? __ldg(crow + k) : B2W_NONE;
-      const uint32_t pos = lower_bound_u32(prow, pdeg, x, lgp);
-      const bool found = pos < pdeg && __ldg(prow + pos) == x;
+      bool found;
+      lower_bound_eq<G == 32>(prow, pdeg, x, kp2, found);
       const bool isprev = valid && (x == prev);
       const uint32_t bprev = T.ballot(isprev);
       if (bprev) kp = c0 + __ffs(bprev) - 1;
@@ -110,8 +157,8 @@ __device__ __forceinline__ uint32_t membership_bitmap(const Tile<G>& T, const ui
       const uint32_t k = c0 + T.tl;
       const bool valid = k < d;
       const uint32_t x = valid ? __ldg(crow + k) : B2W_NONE;
-      const uint32_t pos = lower_bound_u32(prow, pdeg, x, lgp);
-      const bool found = pos < pdeg && __ldg(prow + pos) == x;
+      bool found;
+      lower_bound_eq<G == 32>(prow, pdeg, x, kp2, found);
       const bool isprev = valid && (x == prev);
       const uint32_t bprev = T.ballot(isprev);
       if (bprev) kp = c0 + __ffs(bprev) - 1;
@@ -130,8 +177,9 @@ __device__ __forceinline__ uint32_t membership_bitmap(const Tile<G>& T, const ui
       const uint32_t ii = c0 + T.tl;
       const bool valid = ii < nkeys;
       const uint32_t y = valid ? (ii < pdeg ? __ldg(prow + ii) : prev) : B2W_NONE;
-      const uint32_t pos = lower_bound_u32(crow, d, y, lgd);
-      if (valid && pos < d && __ldg(crow + pos) == y) {
+      bool found;
+      const uint32_t pos = lower_bound_eq<G == 32>(crow, d, y, kd2, found);
+      if (valid && found) {
         if (ii == pdeg) kploc = pos;
         else if (y != prev) { atomicOr(&bm[pos >> 5], 1u << (pos & 31)); ++mloc; }
       }

@@ -41,7 +41,8 @@ constexpr uint32_t NONE = B2W_NONE;
 
 struct UwConsts {
   float w_out, w_ret;                // f32(1/q), f32(1/p)
-  int out_pow2, ret_pow2;            // w_out / w_ret are powers of two in [2^-20, 2^20]: fdiv(w,S) == fa * w
+  float g;                           // common grid of the three weights: a power of two with 1, w_out, w_ret in g Z
+  uint32_t a_in, a_out, a_ret;       // 1 / g, w_out / g, w_ret / g  (exact integers, (max_degree + 1) max(a) < 2^24)
   uint32_t gbm_stride;               // words of global bitmap scratch per group (0: never needed)
   uint32_t* gbm;                     // global bitmap scratch
 };
@@ -133,31 +134,39 @@ __device__ __forceinline__ uint32_t uw_step(const Tile<G>& T, const WalkParams& 
                                             const uint32_t* __restrict__ prow, const uint32_t pdeg, const uint32_t prev,
                                             const bool has_prev, const double u, uint32_t* __restrict__ bm,
                                             uint32_t& st_replays, uint32_t& st_overflow) {
-  const double EC = 1.01 * 5.9604644775390625e-08;                    // 1.01 * 2^-24
   const uint32_t nwords = (d + 31) >> 5;
   // ---------------- phase 1: membership bitmap over the positions of row(cur)
   uint32_t m = 0, kp = NONE, word0 = 0;
   bool in_regs = false;
   if (has_prev) m = membership_bitmap<G>(T, crow, d, prow, pdeg, prev, bm, kp, word0, in_regs);
 
-  // ---------------- phase 2: exact normaliser, three-valued probabilities
-  const float w_o = has_prev ? C.w_out : 1.0f;                    // first step: every weight is 1
+  // ---------------- phase 2: exact normaliser, in integer units of the common weight grid g
+  // W_k = (k+1) a_o + n_in(k) (a_in - a_o) + [kp <= k] (a_ret - a_o): the exact un-normalised prefix (< 2^24, host
+  // verified), W_d = W_{d-1} the exact total; S = W_d g is the reference's sequential f32 sum (no partial sum rounds).
+  // Differences are taken modulo 2^32; every true value is a small non-negative integer.
+  const uint32_t a_o = has_prev ? C.a_out : C.a_in;                // first step: every weight is 1
+  const uint32_t da = C.a_in - a_o, dr = C.a_ret - a_o;
   const uint32_t h = (kp != NONE) ? 1u : 0u;
-  const uint32_t n_o = d - m - h;
-  const double Tw = fma((double)n_o, (double)w_o, fma((double)h, (double)C.w_ret, (double)m));   // exact
-  const float S = (float)Tw;                                      // exact (host-verified precondition)
-  const float fa = __fdiv_rn(1.0f, S);
-  const float fo = !has_prev ? fa : (C.out_pow2 ? __fmul_rn(fa, w_o) : __fdiv_rn(w_o, S));
-  const float fp = C.ret_pow2 ? __fmul_rn(fa, C.w_ret) : __fdiv_rn(C.w_ret, S);
-  const double po = (double)fo, dpa = (double)fa - po, dpp = (double)fp - po;
+  const uint32_t Wd = d * a_o + m * da + h * dr;
 
+  // ---------------- phase 3: filter.  The reference's cdf_k = f32 sequential cumsum of fdiv(w_i, S) satisfies
+  //   cdf_k = (W_k / W_d)(1 + t),  |t| <= e_k := 1.02 (k + 3) 2^-24      ((k+3) 2^-24 <= 0.01; one fdiv + k additions)
+  // so with A = u W_d:   W_k < A (1 - e)          => cdf_k < u   (1 - e <= 1 / (1 + e))
+  //                      W_k >= A (1 + e + 2 e^2) => cdf_k >= u  (1 / (1 - e) <= 1 + e + 2 e^2)
+  // for any e >= e_k.  W_k is an integer, so both tests are integer compares against ceil() of the two thresholds;
+  // the thresholds are uniform per row (word level) / per word (position level) and are pushed outwards by 2^-45
+  // relative, far more than the f64 rounding of the three products.  The first k that is "possible" is the
+  // reference's choice if it is also "sure"; otherwise (probability ~ e W_d per step) the exact replay decides.
+  const double EC = 1.02 * 5.9604644775390625e-08;                    // 1.02 * 2^-24
+  const double A = u * (double)Wd;
   uint32_t choice = d;                                            // default: cdf[-1] < u (overflow)
-  bool replay = (P.flags & B2W_FLAG_FORCE_EXACT_REPLAY) != 0;
+  bool replay = (P.flags & B2W_FLAG_FORCE_EXACT_REPLAY) != 0 || d > 160000u;
   if (!replay) {
-    // T_k = (k+1) po + n_in(k) (pa - po) + [kp <= k] (pp - po), all in f64 (filter arithmetic only)
     uint32_t wsel = 0, bits_sel = 0, nc_before = 0;
     if (nwords > 1) {
-      // word level: first word whose last position possibly reaches u
+      // word level: first word whose last position possibly reaches u (row-uniform, most conservative threshold)
+      const double e_row = EC * (double)(d + 2);
+      const uint32_t P_row = (uint32_t)ceil(A * (1.0 - e_row - 2.9e-14));
       uint32_t carry = 0;
       wsel = NONE;
       for (uint32_t w0 = 0; w0 < nwords; w0 += G) {
@@ -167,10 +176,8 @@ __device__ __forceinline__ uint32_t uw_step(const Tile<G>& T, const WalkParams& 
         const uint32_t cnt = __popc(bits);
         const uint32_t incl = T.incl_scan(cnt) + carry;
         const uint32_t kend = min(d, (w + 1) << 5) - 1;
-        double Tk = fma((double)(kend + 1), po, (double)incl * dpa);
-        if (kp <= kend) Tk += dpp;                                // NONE compares false
-        const double hi_b = fma(Tk, EC * (double)(kend + 2), Tk);
-        const uint32_t bal = T.ballot(valid && (hi_b >= u));
+        const uint32_t Wk = (kend + 1) * a_o + incl * da + (kp <= kend ? dr : 0u);   // NONE compares false
+        const uint32_t bal = T.ballot(valid && Wk >= P_row);
         if (bal) {
           const int src = __ffs(bal) - 1;
           wsel = w0 + src;
@@ -185,29 +192,37 @@ __device__ __forceinline__ uint32_t uw_step(const Tile<G>& T, const WalkParams& 
     }
     if (wsel != NONE) {
       // position level inside the selected word
-      bool decided = false;
       const uint32_t nb = min(32u, d - (wsel << 5));
+      const double e_w = EC * (double)((wsel << 5) + nb + 2);
+      const uint32_t P_w = (uint32_t)ceil(A * (1.0 - e_w - 2.9e-14));
+      const uint32_t Q_w = (uint32_t)ceil(A * (1.0 + e_w + 2.0 * e_w * e_w + 2.9e-14));
+      bool decided = false;
       for (uint32_t r0 = 0; r0 < nb && !decided; r0 += G) {
         const uint32_t b = r0 + T.tl;
         const uint32_t k = (wsel << 5) + b;
         const bool valid = b < nb;
         const uint32_t nc = nc_before + __popc(bits_sel & (0xFFFFFFFFu >> (31 - (b & 31))));
-        double Tk = fma((double)(k + 1), po, (double)nc * dpa);
-        if (kp <= k) Tk += dpp;
-        const double Ek = Tk * (EC * (double)(k + 2));
-        const uint32_t bp = T.ballot(valid && (Tk + Ek >= u));
+        const uint32_t Wk = (k + 1) * a_o + nc * da + (kp <= k ? dr : 0u);
+        const uint32_t bp = T.ballot(valid && Wk >= P_w);
         if (bp) {
           const int f = __ffs(bp) - 1;
-          const bool sure = T.shfl((Tk - Ek >= u) ? 1 : 0, f) != 0;
+          const bool sure = T.shfl((Wk >= Q_w) ? 1 : 0, f) != 0;
           if (sure) choice = (wsel << 5) + r0 + f; else replay = true;
           decided = true;
         }
       }
       if (!decided) replay = true;                               // rounding at the word boundary
+    } else {
+      replay = true;                                               // no word reaches the row threshold (u ~ 1)
     }
   }
   if (replay) {
     if (in_regs) { if (T.tl == 0) bm[0] = word0; T.sync(); }      // the replay reads the bitmap from memory
+    // the reference's probabilities: three exact f32 quotients by S = W_d g (rw/sparse_rw.py:89)
+    const float S = __fmul_rn(__uint2float_rn(Wd), C.g);           // exact: W_d < 2^24, g a power of two
+    const float fa = __fdiv_rn(1.0f, S);
+    const float fo = has_prev ? __fdiv_rn(C.w_out, S) : fa;
+    const float fp = __fdiv_rn(C.w_ret, S);
     choice = replay_exact<G>(bm, has_prev, nwords, d, kp, fa, fo, fp, u);
     ++st_replays;
   }
@@ -223,8 +238,6 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_kernel(const WalkPar
   __shared__ uint32_t s_bm[GROUPS][UW_BW];
   const Tile<G> T;
   const int gib = threadIdx.x / G;                                   // group in block
-  const uint32_t ggid = blockIdx.x * GROUPS + gib;                    // global group id
-  uint32_t* const gbm = C.gbm + (size_t)ggid * C.gbm_stride;
   const uint32_t L = P.L;
   uint32_t st_steps = 0, st_replays = 0, st_overflow = 0;
 
@@ -253,7 +266,9 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_kernel(const WalkPar
       const double u = T.shfl(my_u, (j - 1) & (G - 1));
       const bool has_prev = j > 1;
       const uint32_t nwords = (d + 31) >> 5;
-      uint32_t* const bm = (nwords <= UW_BW) ? s_bm[gib] : gbm;
+      uint32_t* bm = s_bm[gib];
+      if (nwords > UW_BW)                                             // hub row: this group's global scratch (rare)
+        bm = C.gbm + (size_t)(blockIdx.x * GROUPS + gib) * C.gbm_stride;
       const uint32_t* const crow = P.indices + cs;
 
       const uint32_t choice = uw_step<G>(T, P, C, crow, d, prow, pdeg, prev, has_prev, u, bm, st_replays, st_overflow);
@@ -445,9 +460,9 @@ uint32_t gbm_stride(const b2w_graph* g) {
 
 }  // namespace
 
-// Exactness precondition of the analytic normaliser: 1, f32(1/q), f32(1/p) are multiples of one
-// power of two g and (max_degree + 1) * max(w) < 2^24 g.
-bool b2w_uw_eligible(const b2w_graph* g, double p, double q) {
+// Exactness precondition of the analytic normaliser: 1, f32(1/q), f32(1/p) are multiples of one power of two g
+// and (max_degree + 1) * max(w) < 2^24 g.  Returns the exponent of g through `grid_exp` when eligible.
+static bool uw_grid(const b2w_graph* g, double p, double q, int* grid_exp) {
   if (!(g->flags & B2W_GRAPH_UNWEIGHTED)) return false;
   const float w[3] = {1.0f, (float)(1.0 / q), (float)(1.0 / p)};
   int low = 1000;
@@ -464,9 +479,14 @@ bool b2w_uw_eligible(const b2w_graph* g, double p, double q) {
     if (e < low) low = e;
     if (v > mx) mx = v;
   }
+  if (low < -100 || low > 100) return false;
   double lim = ldexp(1.0, 24 + low);
-  return ((double)g->max_degree + 1.0) * (double)mx < lim;
+  if (!(((double)g->max_degree + 1.0) * (double)mx < lim)) return false;
+  if (grid_exp) *grid_exp = low;
+  return true;
 }
+
+bool b2w_uw_eligible(const b2w_graph* g, double p, double q) { return uw_grid(g, p, q, nullptr); }
 
 size_t b2w_uw_work_bytes(const b2w_graph* g) {
   return 256 + (size_t)max_groups(g) * gbm_stride(g) * sizeof(uint32_t);
@@ -479,9 +499,12 @@ int b2w_launch_uw(const b2w_graph* g, const WalkParams& P_in, cudaStream_t s) {
   UwConsts C;
   C.w_out = (float)(1.0 / P.q);
   C.w_ret = (float)(1.0 / P.p);
-  auto pow2 = [](float v) { int e; float mnt = frexpf(v, &e); return mnt == 0.5f && e >= -19 && e <= 21; };
-  C.out_pow2 = pow2(C.w_out) ? 1 : 0;
-  C.ret_pow2 = pow2(C.w_ret) ? 1 : 0;
+  int gexp = 0;
+  if (!uw_grid(g, P.p, P.q, &gexp)) { b2w_set_error("walk_uw_kernel: graph / p / q not eligible"); return B2W_ERR_INVALID; }
+  C.g = ldexpf(1.0f, gexp);
+  C.a_in = (uint32_t)ldexp(1.0, -gexp);                              // exact integers by construction of g
+  C.a_out = (uint32_t)ldexp((double)C.w_out, -gexp);
+  C.a_ret = (uint32_t)ldexp((double)C.w_ret, -gexp);
   C.gbm = reinterpret_cast<uint32_t*>(base + 256);
   C.gbm_stride = gbm_stride(g);
   B2W_CUDA(cudaMemsetAsync(P.counter, 0, 8, s));

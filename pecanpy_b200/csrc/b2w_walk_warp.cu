@@ -77,7 +77,7 @@ __device__ __forceinline__ uint32_t otf_choice_warp(const WalkParams& P, const T
   }
 
   // ---- phase 2: stream the weights, stage w, one partial sum per chunk
-  const uint32_t lgp = 32 - __clz(pdeg);
+  const uint32_t kp2 = 31 - __clz(pdeg | 1u);                                 // floor(log2 pdeg) (first step: pdeg = 0, unused)
   float thr_cur = 0.f;
   if (EXTEND && has_prev) thr_cur = __ldg(P.thr + cur);
   for (uint32_t c = 0; c < nchunks; ++c) {
@@ -95,8 +95,8 @@ __device__ __forceinline__ uint32_t otf_choice_warp(const WalkParams& P, const T
         }
       } else {
         const uint32_t x = valid ? __ldg(crow + k) : B2W_NONE;
-        const uint32_t pos = lower_bound_u32(prow, pdeg, x, lgp);
-        const bool common = pos < pdeg && __ldg(prow + pos) == x;
+        bool common;
+        const uint32_t pos = lower_bound_eq<true>(prow, pdeg, x, kp2, common);
         if (valid) {
           if (x == prev) {
             w = div_by(wt, P.p, P.invp_f, P.p_pow2);                           // (:126)
