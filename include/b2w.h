@@ -69,6 +69,7 @@ typedef enum {
 #define B2W_FLAG_NO_UNWEIGHTED_KERNEL 0x8u /* SparseOTF: always use the generic (weight-streaming) kernel */
 #define B2W_FLAG_NO_TMA 0x10u /* DenseOTF: per-lane vector loads instead of cp.async.bulk staging */
 #define B2W_FLAG_COOP 0x20u /* unweighted SparseOTF, G < 32: warp-cooperative state-machine kernel (long rows by all 32 lanes) */
+#define B2W_FLAG_L2_PERSIST 0x40u /* unweighted SparseOTF: launch with an L2 persisting access window over `indices` */
 #define B2W_FLAG_GROUP(n) (((uint32_t)(n) & 0xFFu) << 8) /* tuning: lanes per walker (8/16/32), 0 = auto */
 
 typedef struct b2w_graph b2w_graph; /* opaque */

@@ -9,7 +9,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb2w.so")
+# B2W_LIBRARY: developer knob for A/B runs of tuning variants built by tools/build_variants.py (same ABI, same
+# CUDA code base compiled with a different -D); unset in normal use.
+LIB_PATH = os.environ.get("B2W_LIBRARY") or os.path.join(_HERE, "lib", "libb2w.so")
 
 OK = 0
 MODE_SPARSE_OTF, MODE_PRECOMP, MODE_DENSE_OTF, MODE_FIRST_ORDER_UNWEIGHTED, MODE_PRECOMP_FIRST_ORDER = range(5)
@@ -20,6 +22,7 @@ FLAG_THREAD_PER_WALKER = 0x4
 FLAG_NO_UNWEIGHTED_KERNEL = 0x8
 FLAG_NO_TMA = 0x10
 FLAG_COOP = 0x20
+FLAG_L2_PERSIST = 0x40
 
 
 def FLAG_GROUP(n: int) -> int:

@@ -61,19 +61,21 @@ def build_pylists(force: bool = False) -> str:
     return out
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str = LIB, obj_dir: str = OBJ_DIR) -> str:
+    """Compile every .cu for sm_100a and link the shared library.  `extra_flags` / `out` / `obj_dir` build a tuning
+    variant (e.g. ``-DB2W_UW_NESTED=0``) next to the product library; see tools/build_variants.py."""
     build_pylists(force)
-    if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _deps_mtime():
-        return LIB
-    os.makedirs(OBJ_DIR, exist_ok=True)
-    os.makedirs(LIB_DIR, exist_ok=True)
+    if not force and os.path.exists(out) and os.path.getmtime(out) >= _deps_mtime():
+        return out
+    os.makedirs(obj_dir, exist_ok=True)
+    os.makedirs(os.path.dirname(out), exist_ok=True)
     nvcc = _nvcc()
     env = dict(os.environ)
     env.pop("CC", None)   # the image's $CC is not a usable nvcc host compiler selector
 
     def compile_one(src: str):
-        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)
         return src, obj, r
 
@@ -85,16 +87,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
             objs.append(obj)
-    with open(os.path.join(OBJ_DIR, "ptxas.log"), "w") as f:
+    with open(os.path.join(obj_dir, "ptxas.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    tmp = LIB + ".tmp"
+    tmp = out + ".tmp"
     r = subprocess.run([nvcc, "-shared", "-o", tmp, *objs], capture_output=True, text=True, env=env)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    os.replace(tmp, LIB)
-    return LIB
+    os.replace(tmp, out)
+    return out
 
 
 if __name__ == "__main__":

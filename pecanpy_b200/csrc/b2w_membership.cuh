@@ -64,7 +64,10 @@ struct Tile {
   }
 // WARP_UNIFORM (k is the same for all 32 lanes, i.e. 32-lane groups): jump into the unrolled probe sequence.
 // Sub-warp groups have different k per group; jumping to different entry points would serialise the groups
-// of a warp, so they run a counted loop instead (lanes that finish early wait at the loop exit).
+// of a warp, so they run a counted loop instead (lanes that finish early wait at the loop exit).  The unrolled
+// form costs ~330 instructions of code per inlined copy; the generic weight-streaming kernel (already 2760
+// instructions) went from 0.63 to 0.48 G steps/s with it -- instruction-cache misses became its second largest
+// stall -- and uses the loop form too.
 template <bool WARP_UNIFORM>
 __device__ __forceinline__ uint32_t lower_bound_eq(const uint32_t* __restrict__ row, const uint32_t n, const uint32_t x,
                                                    const uint32_t k, bool& found) {
@@ -106,6 +109,30 @@ __device__ __forceinline__ uint32_t lower_bound_eq(const uint32_t* __restrict__ 
 #undef B2W_LB_PROBE
 
 
+// Two independent searches in the same row, interleaved probe by probe: the dependent-load chain of a search
+// (k + 1 loads, each an L1/L2 round trip on a hub row) is what a multi-chunk membership step waits for, and two
+// chunks in flight halve the number of such chains per step.
+__device__ __forceinline__ void lower_bound_eq_x2(const uint32_t* __restrict__ row, const uint32_t n, const uint32_t x0,
+                                                  const uint32_t x1, const uint32_t k, uint32_t& lo0, bool& f0,
+                                                  uint32_t& lo1, bool& f1) {
+  const uint32_t top = 1u << k;
+  const uint32_t v = __ldg(row + (top - 1));
+  uint32_t ge0 = (v < x0) ? B2W_NONE : v, ge1 = (v < x1) ? B2W_NONE : v;
+  lo0 = (v < x0) ? n - top + 1 : 0u;
+  lo1 = (v < x1) ? n - top + 1 : 0u;
+  for (uint32_t S = top >> 1; S; S >>= 1) {
+    const uint32_t a = __ldg(row + (lo0 + S - 1u)), b = __ldg(row + (lo1 + S - 1u));
+    if (a < x0) lo0 += S; else ge0 = a;
+    if (b < x1) lo1 += S; else ge1 = b;
+  }
+  f0 = ge0 == x0;
+  f1 = ge1 == x1;
+}
+#ifndef B2W_DUAL_CHUNKS
+#define B2W_DUAL_CHUNKS 0
+#endif
+
+
 // Membership of the neighbours of `cur` in N(prev) as a BITMAP over the positions of row(cur)
 // (rows sorted and duplicate-free, for which the reference's merge `isnotin`, rw/sparse_rw.py:142-230,
 // is exactly set membership).  Searches whichever side needs fewer probes:
@@ -117,7 +144,7 @@ __device__ __forceinline__ uint32_t lower_bound_eq(const uint32_t* __restrict__ 
 // Returns the number of common neighbours.  Rows of at most 32 entries return their single bitmap word in
 // `word0` (in_regs = true, nothing written to `bm`); otherwise the bitmap is in `bm` and the function ends with a
 // group sync so that it is visible to all lanes.
-template <int G>
+template <int G, bool UNROLLED_SEARCH = false>
 __device__ __forceinline__ uint32_t membership_bitmap(const Tile<G>& T, const uint32_t* __restrict__ crow,
                                                       const uint32_t d, const uint32_t* __restrict__ prow,
                                                       const uint32_t pdeg, const uint32_t prev,
@@ -141,10 +168,9 @@ __device__ __forceinline__ uint32_t membership_bitmap(const Tile<G>& T, const ui
       const bool valid = k < d;
       const uint32_t x = valid ? __ldg(crow + k) : B2W_NONE;
       bool found;
-      lower_bound_eq<G == 32>(prow, pdeg, x, kp2, found);
+      lower_bound_eq<UNROLLED_SEARCH>(prow, pdeg, x, kp2, found);
       const bool isprev = valid && (x == prev);
-      const uint32_t bprev = T.ballot(isprev);
-      if (bprev) kp = c0 + __ffs(bprev) - 1;
+      kp = min(kp, __reduce_min_sync(T.mask, isprev ? k : B2W_NONE));   // one REDUX instead of ballot + ffs + select
       const uint32_t bal = T.ballot(valid && found && !isprev);
       word0 |= (G == 32) ? bal : (bal << c0);
       m += __popc(bal);
@@ -152,16 +178,34 @@ __device__ __forceinline__ uint32_t membership_bitmap(const Tile<G>& T, const ui
     in_regs = true;
     return m;
   }
+  constexpr bool DUAL = (B2W_DUAL_CHUNKS != 0) && G == 32;
   if (d <= 2 * 32 || fwd_cost <= rev_cost) {
-    for (uint32_t c0 = 0; c0 < d; c0 += G) {
+    uint32_t c0 = 0;
+    if (DUAL) {
+      for (; c0 + G < d; c0 += 2 * G) {                               // two chunks of the row per iteration
+        const uint32_t k0 = c0 + T.tl, k1 = k0 + G;
+        const bool valid1 = k1 < d;
+        const uint32_t x0 = __ldg(crow + k0);
+        const uint32_t x1 = valid1 ? __ldg(crow + k1) : B2W_NONE;
+        uint32_t p0, p1;
+        bool f0, f1;
+        lower_bound_eq_x2(prow, pdeg, x0, x1, kp2, p0, f0, p1, f1);
+        const bool isprev0 = x0 == prev, isprev1 = valid1 && (x1 == prev);
+        kp = min(kp, __reduce_min_sync(T.mask, isprev0 ? k0 : (isprev1 ? k1 : B2W_NONE)));
+        const uint32_t bal0 = T.ballot(f0 && !isprev0);
+        const uint32_t bal1 = T.ballot(valid1 && f1 && !isprev1);
+        if (T.tl == 0) { bm[c0 >> 5] = bal0; bm[(c0 >> 5) + 1] = bal1; }
+        m += __popc(bal0) + __popc(bal1);
+      }
+    }
+    for (; c0 < d; c0 += G) {
       const uint32_t k = c0 + T.tl;
       const bool valid = k < d;
       const uint32_t x = valid ? __ldg(crow + k) : B2W_NONE;
       bool found;
-      lower_bound_eq<G == 32>(prow, pdeg, x, kp2, found);
+      lower_bound_eq<UNROLLED_SEARCH>(prow, pdeg, x, kp2, found);
       const bool isprev = valid && (x == prev);
-      const uint32_t bprev = T.ballot(isprev);
-      if (bprev) kp = c0 + __ffs(bprev) - 1;
+      kp = min(kp, __reduce_min_sync(T.mask, isprev ? k : B2W_NONE));   // one REDUX instead of ballot + ffs + select
       const uint32_t bal = T.ballot(valid && found && !isprev);
       if (T.tl == 0) {
         if (G == 32 || (c0 & 31) == 0) bm[c0 >> 5] = bal; else bm[c0 >> 5] |= bal << (c0 & 31);
@@ -173,12 +217,32 @@ __device__ __forceinline__ uint32_t membership_bitmap(const Tile<G>& T, const ui
     T.sync();
     const uint32_t nkeys = pdeg + 1;
     uint32_t mloc = 0, kploc = B2W_NONE;
-    for (uint32_t c0 = 0; c0 < nkeys; c0 += G) {
+    uint32_t c0 = 0;
+    if (DUAL) {
+      for (; c0 + G < nkeys; c0 += 2 * G) {                           // two chunks of keys per iteration
+        const uint32_t i0 = c0 + T.tl, i1 = i0 + G;
+        const bool valid1 = i1 < nkeys;
+        const uint32_t y0 = i0 < pdeg ? __ldg(prow + i0) : prev;
+        const uint32_t y1 = valid1 ? (i1 < pdeg ? __ldg(prow + i1) : prev) : B2W_NONE;
+        uint32_t p0, p1;
+        bool f0, f1;
+        lower_bound_eq_x2(crow, d, y0, y1, kd2, p0, f0, p1, f1);
+        if (f0) {
+          if (i0 == pdeg) kploc = p0;
+          else if (y0 != prev) { atomicOr(&bm[p0 >> 5], 1u << (p0 & 31)); ++mloc; }
+        }
+        if (valid1 && f1) {
+          if (i1 == pdeg) kploc = p1;
+          else if (y1 != prev) { atomicOr(&bm[p1 >> 5], 1u << (p1 & 31)); ++mloc; }
+        }
+      }
+    }
+    for (; c0 < nkeys; c0 += G) {
       const uint32_t ii = c0 + T.tl;
       const bool valid = ii < nkeys;
       const uint32_t y = valid ? (ii < pdeg ? __ldg(prow + ii) : prev) : B2W_NONE;
       bool found;
-      const uint32_t pos = lower_bound_eq<G == 32>(crow, d, y, kd2, found);
+      const uint32_t pos = lower_bound_eq<UNROLLED_SEARCH>(crow, d, y, kd2, found);
       if (valid && found) {
         if (ii == pdeg) kploc = pos;
         else if (y != prev) { atomicOr(&bm[pos >> 5], 1u << (pos & 31)); ++mloc; }

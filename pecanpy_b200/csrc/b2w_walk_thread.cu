@@ -19,8 +19,10 @@ __device__ __forceinline__ uint32_t alias_draw(const uint32_t* __restrict__ j, c
   return (u < (double)qv) ? kk : j[off + kk];
 }
 
-template <int MODE, bool EXTEND>
-__global__ void __launch_bounds__(256) walk_thread_kernel(const WalkParams P) {
+// MINB = minimum resident CTAs per SM (register cap): the PreComp step is a chain of ~6 dependent gathers, so
+// what it wants is warps in flight, not registers.
+template <int MODE, bool EXTEND, int MINB>
+__global__ void __launch_bounds__(256, MINB) walk_thread_kernel(const WalkParams P) {
   const uint32_t L = P.L;
   uint64_t steps = 0, overflow = 0;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < P.n_rows;
@@ -87,14 +89,14 @@ __global__ void __launch_bounds__(256) walk_thread_kernel(const WalkParams P) {
   }
 }
 
-template <int MODE, bool EXTEND>
+template <int MODE, bool EXTEND, int MINB = 1>
 int launch(const b2w_graph* g, const WalkParams& P, cudaStream_t s) {
   int threads = 256;
   uint64_t want = (P.n_rows + threads - 1) / threads;
   uint64_t cap = (uint64_t)g->num_sms * 8 * 4;   // grid-stride beyond a few waves
   int blocks = (int)(want < cap ? want : cap);
   if (blocks < 1) blocks = 1;
-  walk_thread_kernel<MODE, EXTEND><<<blocks, threads, 0, s>>>(P);
+  walk_thread_kernel<MODE, EXTEND, MINB><<<blocks, threads, 0, s>>>(P);
   return b2w_cuda_fail(cudaGetLastError(), "walk_thread_kernel launch");
 }
 
@@ -104,7 +106,14 @@ int b2w_launch_thread_walk(const b2w_graph* g, int mode, int extend, const WalkP
   switch (mode) {
     case B2W_MODE_SPARSE_OTF:
       return extend ? launch<B2W_MODE_SPARSE_OTF, true>(g, P, s) : launch<B2W_MODE_SPARSE_OTF, false>(g, P, s);
-    case B2W_MODE_PRECOMP: return launch<B2W_MODE_PRECOMP, false>(g, P, s);
+    case B2W_MODE_PRECOMP: {
+      // measured on BASELINE config #4 (G steps/s): 64 regs / 4 CTAs 19.0, 48 / 5 20.2, 40 / 6 17.8, 32 / 8 17.6
+      const int mb = (int)((P.flags >> 16) & 0xF);                     // tuning: resident CTAs per SM (0 = default)
+      if (mb == 4) return launch<B2W_MODE_PRECOMP, false, 1>(g, P, s);
+      if (mb == 6) return launch<B2W_MODE_PRECOMP, false, 6>(g, P, s);
+      if (mb == 8) return launch<B2W_MODE_PRECOMP, false, 8>(g, P, s);
+      return launch<B2W_MODE_PRECOMP, false, 5>(g, P, s);
+    }
     case B2W_MODE_FIRST_ORDER_UNWEIGHTED: return launch<B2W_MODE_FIRST_ORDER_UNWEIGHTED, false>(g, P, s);
     case B2W_MODE_PRECOMP_FIRST_ORDER: return launch<B2W_MODE_PRECOMP_FIRST_ORDER, false>(g, P, s);
   }

@@ -129,7 +129,8 @@ __device__ __noinline__ uint32_t replay_exact(const uint32_t* __restrict__ bm, c
 // exact replay.  All arguments are group-uniform; `bm` is a group-private bitmap of >= ceil(d / 32) words.
 // Returns the reference's `choice` (== d for its cdf[-1] < u overflow).  Ends with a group sync.
 template <int G>
-__device__ __forceinline__ uint32_t uw_step(const Tile<G>& T, const WalkParams& P, const UwConsts& C,
+__device__ __forceinline__ uint32_t uw_step(const Tile<G>& T, const uint32_t flags, const uint32_t a_in,
+                                            const uint32_t a_out, const uint32_t a_ret, const float grid,
                                             const uint32_t* __restrict__ crow, const uint32_t d,
                                             const uint32_t* __restrict__ prow, const uint32_t pdeg, const uint32_t prev,
                                             const bool has_prev, const double u, uint32_t* __restrict__ bm,
@@ -138,14 +139,14 @@ __device__ __forceinline__ uint32_t uw_step(const Tile<G>& T, const WalkParams& 
   // ---------------- phase 1: membership bitmap over the positions of row(cur)
   uint32_t m = 0, kp = NONE, word0 = 0;
   bool in_regs = false;
-  if (has_prev) m = membership_bitmap<G>(T, crow, d, prow, pdeg, prev, bm, kp, word0, in_regs);
+  if (has_prev) m = membership_bitmap<G, G == 32>(T, crow, d, prow, pdeg, prev, bm, kp, word0, in_regs);
 
   // ---------------- phase 2: exact normaliser, in integer units of the common weight grid g
   // W_k = (k+1) a_o + n_in(k) (a_in - a_o) + [kp <= k] (a_ret - a_o): the exact un-normalised prefix (< 2^24, host
   // verified), W_d = W_{d-1} the exact total; S = W_d g is the reference's sequential f32 sum (no partial sum rounds).
   // Differences are taken modulo 2^32; every true value is a small non-negative integer.
-  const uint32_t a_o = has_prev ? C.a_out : C.a_in;                // first step: every weight is 1
-  const uint32_t da = C.a_in - a_o, dr = C.a_ret - a_o;
+  const uint32_t a_o = has_prev ? a_out : a_in;                    // first step: every weight is 1
+  const uint32_t da = a_in - a_o, dr = a_ret - a_o;
   const uint32_t h = (kp != NONE) ? 1u : 0u;
   const uint32_t Wd = d * a_o + m * da + h * dr;
 
@@ -153,20 +154,20 @@ __device__ __forceinline__ uint32_t uw_step(const Tile<G>& T, const WalkParams& 
   //   cdf_k = (W_k / W_d)(1 + t),  |t| <= e_k := 1.02 (k + 3) 2^-24      ((k+3) 2^-24 <= 0.01; one fdiv + k additions)
   // so with A = u W_d:   W_k < A (1 - e)          => cdf_k < u   (1 - e <= 1 / (1 + e))
   //                      W_k >= A (1 + e + 2 e^2) => cdf_k >= u  (1 / (1 - e) <= 1 + e + 2 e^2)
-  // for any e >= e_k.  W_k is an integer, so both tests are integer compares against ceil() of the two thresholds;
-  // the thresholds are uniform per row (word level) / per word (position level) and are pushed outwards by 2^-45
-  // relative, far more than the f64 rounding of the three products.  The first k that is "possible" is the
+  // for any e >= e_k.  W_k is an exact integer (exact in f64 too); the two thresholds are uniform per row (word
+  // level) / per word (position level) and are pushed outwards by 2^-45 relative, far more than the f64 rounding
+  // of the three products, so a lane only converts its W_k and compares.  The first k that is "possible" is the
   // reference's choice if it is also "sure"; otherwise (probability ~ e W_d per step) the exact replay decides.
   const double EC = 1.02 * 5.9604644775390625e-08;                    // 1.02 * 2^-24
   const double A = u * (double)Wd;
   uint32_t choice = d;                                            // default: cdf[-1] < u (overflow)
-  bool replay = (P.flags & B2W_FLAG_FORCE_EXACT_REPLAY) != 0 || d > 160000u;
+  bool replay = (flags & B2W_FLAG_FORCE_EXACT_REPLAY) != 0 || d > 160000u;
   if (!replay) {
     uint32_t wsel = 0, bits_sel = 0, nc_before = 0;
     if (nwords > 1) {
       // word level: first word whose last position possibly reaches u (row-uniform, most conservative threshold)
       const double e_row = EC * (double)(d + 2);
-      const uint32_t P_row = (uint32_t)ceil(A * (1.0 - e_row - 2.9e-14));
+      const double t_row = A * (1.0 - e_row - 2.9e-14);
       uint32_t carry = 0;
       wsel = NONE;
       for (uint32_t w0 = 0; w0 < nwords; w0 += G) {
@@ -177,7 +178,7 @@ __device__ __forceinline__ uint32_t uw_step(const Tile<G>& T, const WalkParams& 
         const uint32_t incl = T.incl_scan(cnt) + carry;
         const uint32_t kend = min(d, (w + 1) << 5) - 1;
         const uint32_t Wk = (kend + 1) * a_o + incl * da + (kp <= kend ? dr : 0u);   // NONE compares false
-        const uint32_t bal = T.ballot(valid && Wk >= P_row);
+        const uint32_t bal = T.ballot(valid && (double)Wk >= t_row);
         if (bal) {
           const int src = __ffs(bal) - 1;
           wsel = w0 + src;
@@ -194,8 +195,8 @@ __device__ __forceinline__ uint32_t uw_step(const Tile<G>& T, const WalkParams& 
       // position level inside the selected word
       const uint32_t nb = min(32u, d - (wsel << 5));
       const double e_w = EC * (double)((wsel << 5) + nb + 2);
-      const uint32_t P_w = (uint32_t)ceil(A * (1.0 - e_w - 2.9e-14));
-      const uint32_t Q_w = (uint32_t)ceil(A * (1.0 + e_w + 2.0 * e_w * e_w + 2.9e-14));
+      const double t_poss = A * (1.0 - e_w - 2.9e-14);
+      const double t_sure = A * (1.0 + e_w + 2.0 * e_w * e_w + 2.9e-14);
       bool decided = false;
       for (uint32_t r0 = 0; r0 < nb && !decided; r0 += G) {
         const uint32_t b = r0 + T.tl;
@@ -203,10 +204,11 @@ __device__ __forceinline__ uint32_t uw_step(const Tile<G>& T, const WalkParams& 
         const bool valid = b < nb;
         const uint32_t nc = nc_before + __popc(bits_sel & (0xFFFFFFFFu >> (31 - (b & 31))));
         const uint32_t Wk = (k + 1) * a_o + nc * da + (kp <= k ? dr : 0u);
-        const uint32_t bp = T.ballot(valid && Wk >= P_w);
+        const double Wkd = (double)Wk;
+        const uint32_t bp = T.ballot(valid && Wkd >= t_poss);
         if (bp) {
           const int f = __ffs(bp) - 1;
-          const bool sure = T.shfl((Wk >= Q_w) ? 1 : 0, f) != 0;
+          const bool sure = T.shfl((Wkd >= t_sure) ? 1 : 0, f) != 0;
           if (sure) choice = (wsel << 5) + r0 + f; else replay = true;
           decided = true;
         }
@@ -219,10 +221,10 @@ __device__ __forceinline__ uint32_t uw_step(const Tile<G>& T, const WalkParams& 
   if (replay) {
     if (in_regs) { if (T.tl == 0) bm[0] = word0; T.sync(); }      // the replay reads the bitmap from memory
     // the reference's probabilities: three exact f32 quotients by S = W_d g (rw/sparse_rw.py:89)
-    const float S = __fmul_rn(__uint2float_rn(Wd), C.g);           // exact: W_d < 2^24, g a power of two
-    const float fa = __fdiv_rn(1.0f, S);
-    const float fo = has_prev ? __fdiv_rn(C.w_out, S) : fa;
-    const float fp = __fdiv_rn(C.w_ret, S);
+    const float S = __fmul_rn(__uint2float_rn(Wd), grid);          // exact: W_d < 2^24, g a power of two
+    const float fa = __fdiv_rn(1.0f, S);                           // w_out = a_out g, w_ret = a_ret g, exactly
+    const float fo = has_prev ? __fdiv_rn(__fmul_rn(__uint2float_rn(a_out), grid), S) : fa;
+    const float fp = __fdiv_rn(__fmul_rn(__uint2float_rn(a_ret), grid), S);
     choice = replay_exact<G>(bm, has_prev, nwords, d, kp, fa, fo, fp, u);
     ++st_replays;
   }
@@ -232,6 +234,11 @@ __device__ __forceinline__ uint32_t uw_step(const Tile<G>& T, const WalkParams& 
   return choice;
 }
 
+// (A restructured main loop -- one outer iteration per block of G output entries, Philox and the block store hoisted
+// out of the step loop, hub rows through an out-of-line copy of the step so that the common path only sees a
+// shared-memory bitmap -- executes ~40 fewer instructions per step but needs more live registers than the 48 that
+// 5 CTAs/SM allow: measured 1.59 (out-of-line hub step, 76 B of spills) and 1.79 (inline) vs 1.91 G steps/s for the
+// flat loop below on BASELINE config #3.  Occupancy beats instruction count here: the kernel waits on dependent loads.)
 template <int G, int MINB>
 __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_kernel(const WalkParams P, const UwConsts C) {
   constexpr int GROUPS = UW_THREADS / G;
@@ -271,12 +278,12 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_kernel(const WalkPar
         bm = C.gbm + (size_t)(blockIdx.x * GROUPS + gib) * C.gbm_stride;
       const uint32_t* const crow = P.indices + cs;
 
-      const uint32_t choice = uw_step<G>(T, P, C, crow, d, prow, pdeg, prev, has_prev, u, bm, st_replays, st_overflow);
+      const uint32_t choice = uw_step<G>(T, P.flags, C.a_in, C.a_out, C.a_ret, C.g, crow, d, prow, pdeg, prev, has_prev, u, bm, st_replays, st_overflow);
 
       const uint32_t nxt = __ldg(crow + choice);                      // unchecked, as pecanpy.py:559
       if (T.tl == (j & (G - 1))) myval = nxt;
       if ((j & (G - 1)) == G - 1) {
-        out[(j & ~(uint32_t)(G - 1)) + T.tl] = myval;
+        __stcs(out + ((j & ~(uint32_t)(G - 1)) + T.tl), myval);   // streaming store: keep the graph in L2
         myval = 0u;
       }
       prev = cur; prow = crow; pdeg = d;
@@ -291,7 +298,7 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_kernel(const WalkPar
       const uint32_t e = b0 + T.tl;
       uint32_t v = (b0 == blk) ? myval : 0u;
       if (e == L + 1) v = eff;
-      if (e < L + 2) out[e] = v;
+      if (e < L + 2) __stcs(out + e, v);
     }
   }
   if (P.stats && !(P.flags & B2W_FLAG_NO_FILTER_STATS) && T.tl == 0) {
@@ -343,7 +350,7 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_coop_kernel(const Wa
       const uint32_t e = b0 + T.tl;
       uint32_t v = (b0 == blk) ? myval : 0u;
       if (e == L + 1) v = eff;
-      if (e < L + 2) out[e] = v;
+      if (e < L + 2) __stcs(out + e, v);
     }
     have = false;
   };
@@ -393,19 +400,19 @@ __global__ void __launch_bounds__(UW_THREADS, MINB) walk_uw_coop_kernel(const Wa
       const double b_u = __shfl_sync(B2W_FULL, u, src);
       uint32_t* const bmw = (((b_d + 31) >> 5) <= (uint32_t)UW_BW) ? s_wbm[wib] : gbm;
       uint32_t r2 = 0, o2 = 0;
-      const uint32_t c = uw_step<32>(TW, P, C, P.indices + b_cs, b_d, reinterpret_cast<const uint32_t*>((uintptr_t)b_prow),
+      const uint32_t c = uw_step<32>(TW, P.flags, C.a_in, C.a_out, C.a_ret, C.g, P.indices + b_cs, b_d, reinterpret_cast<const uint32_t*>((uintptr_t)b_prow),
                                      b_pdeg, b_prev, b_hp, b_u, bmw, r2, o2);
       const uint32_t om = (G == 32) ? 0xFFFFFFFFu : (((1u << G) - 1u) << (src & ~(G - 1)));
       if (gmask == om) { choice = c; rep = r2; ovf = o2; }
       bigm &= ~om;
     }
-    if (active && !big) choice = uw_step<G>(T, P, C, crow, d, prow, pdeg, prev, has_prev, u, s_bm[gib], rep, ovf);
+    if (active && !big) choice = uw_step<G>(T, P.flags, C.a_in, C.a_out, C.a_ret, C.g, crow, d, prow, pdeg, prev, has_prev, u, s_bm[gib], rep, ovf);
     if (active) {
       st_replays += rep; st_overflow += ovf;
       const uint32_t nxt = __ldg(crow + choice);                      // unchecked, as pecanpy.py:559
       if (T.tl == (j & (G - 1))) myval = nxt;
       if ((j & (G - 1)) == G - 1) {
-        out[(j & ~(uint32_t)(G - 1)) + T.tl] = myval;
+        __stcs(out + ((j & ~(uint32_t)(G - 1)) + T.tl), myval);   // streaming store: keep the graph in L2
         myval = 0u;
       }
       prev = cur; prow = crow; pdeg = d;
@@ -512,11 +519,34 @@ int b2w_launch_uw(const b2w_graph* g, const WalkParams& P_in, cudaStream_t s) {
   const int MB = (int)((P.flags >> 16) & 0xF);                        // tuning: min resident CTAs per SM (0 = default)
   uint64_t groups_per_block = UW_THREADS / G;
   uint64_t need = (P.n_rows + groups_per_block - 1) / groups_per_block;
+  // B2W_FLAG_L2_PERSIST: per-launch access-policy window that keeps `indices` (the array every probe reads) in the
+  // persisting part of L2, everything else (the streamed walk matrix above all) on the normal / streaming policy.
+  cudaLaunchAttribute attr[1];
+  unsigned n_attr = 0;
+  if ((P.flags & B2W_FLAG_L2_PERSIST) && g->l2_persist_max && g->l2_window_max && g->nnz) {
+    static int limit_set_for = -1;                                     // carve-out is a per-device limit: set it once
+    if (limit_set_for != g->device) {
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, g->l2_persist_max) == cudaSuccess) limit_set_for = g->device;
+      else (void)cudaGetLastError();
+    }
+    size_t bytes = (size_t)g->nnz * sizeof(uint32_t);
+    if (bytes > g->l2_window_max) bytes = g->l2_window_max;
+    attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+    attr[0].val.accessPolicyWindow.base_ptr = const_cast<uint32_t*>(g->indices);
+    attr[0].val.accessPolicyWindow.num_bytes = bytes;
+    attr[0].val.accessPolicyWindow.hitRatio = bytes <= g->l2_persist_max ? 1.0f : (float)((double)g->l2_persist_max / (double)bytes);
+    attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    n_attr = 1;
+  }
 #define B2W_UW_LAUNCH(GG, BB)                                                        \
   do {                                                                               \
     int blocks = grid_blocks<GG, BB>(g);                                             \
     if ((uint64_t)blocks > need) blocks = (int)(need ? need : 1);                    \
-    walk_uw_kernel<GG, BB><<<blocks, UW_THREADS, 0, s>>>(P, C);                      \
+    cudaLaunchConfig_t cfg = {};                                                     \
+    cfg.gridDim = dim3((unsigned)blocks); cfg.blockDim = dim3(UW_THREADS);           \
+    cfg.dynamicSmemBytes = 0; cfg.stream = s; cfg.attrs = attr; cfg.numAttrs = n_attr; \
+    B2W_CUDA(cudaLaunchKernelEx(&cfg, walk_uw_kernel<GG, BB>, P, C));                \
   } while (0)
   // G < 32 with B2W_FLAG_COOP: the cooperative kernel (long rows by the whole warp); bits 20..23 tune BIG = 16 << x
   const uint32_t bigx = (P.flags >> 20) & 0xF;

@@ -96,7 +96,7 @@ __device__ __forceinline__ uint32_t otf_choice_warp(const WalkParams& P, const T
       } else {
         const uint32_t x = valid ? __ldg(crow + k) : B2W_NONE;
         bool common;
-        const uint32_t pos = lower_bound_eq<true>(prow, pdeg, x, kp2, common);
+        const uint32_t pos = lower_bound_eq<false>(prow, pdeg, x, kp2, common);
         if (valid) {
           if (x == prev) {
             w = div_by(wt, P.p, P.invp_f, P.p_pow2);                           // (:126)
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) walk_sparse_warp_kernel
       const uint32_t nxt = __ldg(P.indices + cs + choice);            // unchecked, as pecanpy.py:559
       if (lane == (j & 31)) myval = nxt;
       if ((j & 31) == 31) {                                           // entries [j-31, j] complete: flush
-        out[(j & ~31u) + lane] = myval;
+        __stcs(out + ((j & ~31u) + lane), myval);      // streaming: the 3 GB walk matrix must not evict the graph from L2
         myval = 0u;
       }
       prev = cur; ps = cs; pdeg = deg;
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 4) walk_sparse_warp_kernel
       uint32_t e = base + lane;
       uint32_t v = (base == blk) ? myval : 0u;
       if (e == L + 1) v = eff;
-      if (e < L + 2) out[e] = v;
+      if (e < L + 2) __stcs(out + e, v);
     }
   }
   if (P.stats && !(P.flags & B2W_FLAG_NO_FILTER_STATS) && lane == 0) {

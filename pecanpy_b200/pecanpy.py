@@ -103,10 +103,16 @@ class Base(BaseGraph):
         return [self.nodes[i] for i in walk_idx_ary[:end_idx]]
 
     def simulate_walks(self, num_walks: int, walk_length: int) -> List[List[str]]:
-        mat = self.simulate_walks_array(num_walks, walk_length)
-        ids = np.asarray(self.nodes, dtype=object)
-        lens = mat[:, -1]
-        return [ids[row[:n]].tolist() for row, n in zip(mat, lens)]
+        """Same return value as the reference (pecanpy.py:116-162): one list of node ids per walk, truncated at
+        dead ends.  The id mapping of pecanpy.py:160 is one C loop over the matrix (walks.map_walks)."""
+        from .walks import map_walks
+        return map_walks(self.simulate_walks_array(num_walks, walk_length), self.nodes)
+
+    def simulate_walks_corpus(self, num_walks: int, walk_length: int, block: int = 8192):
+        """The same walks as a lazy, restartable iterable (walks.WalkCorpus): what a streaming consumer such as
+        gensim's Word2Vec needs, without 10^7 Python lists alive at once."""
+        from .walks import WalkCorpus
+        return WalkCorpus(self.simulate_walks_array(num_walks, walk_length), self.nodes, block=block)
 
     def embed(self, dim: int = 128, num_walks: int = 10, walk_length: int = 80, window_size: int = 10,
               epochs: int = 1, verbose: bool = False):
@@ -115,7 +121,7 @@ class Base(BaseGraph):
         except ImportError as exc:  # pragma: no cover - gensim is not part of this image
             raise ImportError("embed() needs gensim (the downstream Word2Vec consumer is out of scope "
                               "for the B200 walk engine; simulate_walks works without it)") from exc
-        walks = self.simulate_walks(num_walks, walk_length)
+        walks = self.simulate_walks_corpus(num_walks, walk_length)
         w2v = Word2Vec(walks, vector_size=dim, window=window_size, sg=1, min_count=0, workers=self.workers,
                        epochs=epochs, seed=self.random_state)
         return w2v.wv[self.nodes]
