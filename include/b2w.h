@@ -69,7 +69,6 @@ typedef enum {
 #define B2W_FLAG_NO_UNWEIGHTED_KERNEL 0x8u /* SparseOTF: always use the generic (weight-streaming) kernel */
 #define B2W_FLAG_NO_TMA 0x10u /* DenseOTF: per-lane vector loads instead of cp.async.bulk staging */
 #define B2W_FLAG_COOP 0x20u /* unweighted SparseOTF, G < 32: warp-cooperative state-machine kernel (long rows by all 32 lanes) */
-#define B2W_FLAG_L2_PERSIST 0x40u /* unweighted SparseOTF: launch with an L2 persisting access window over `indices` */
 #define B2W_FLAG_GROUP(n) (((uint32_t)(n) & 0xFFu) << 8) /* tuning: lanes per walker (8/16/32), 0 = auto */
 
 typedef struct b2w_graph b2w_graph; /* opaque */
@@ -117,6 +116,21 @@ int b2w_graph_dense_create(int device, uint32_t num_nodes, const double* d_data,
 
 int b2w_graph_info_get(const b2w_graph* g, b2w_graph_info* out);
 void b2w_graph_destroy(b2w_graph* g);
+
+/* ---- ingest: edge list -> CSR ------------------------------------------------------------
+ * Replaces the dict-of-dicts build of AdjlstGraph.read / add_edge (graph.py:160-305) + to_csr (graph.py:308-341)
+ * once the text has been parsed into integer endpoints (node numbering by first appearance and the dropping of
+ * non-positive weights stay with the host parser): d_src/d_dst u32[m] and d_weight f64[m] (NULL = unweighted,
+ * every weight 1) in FILE ORDER.  A later edge with the same (row, col) overwrites an earlier one; directed == 0
+ * stores both directions.  Outputs (caller-allocated): d_indptr u32[n+1], d_indices u32 / d_data f32 with room for
+ * m (directed) or 2m (undirected) entries -- allocate one more element of d_indices if the arrays go straight
+ * into b2w_graph_csr_create.  *h_nnz receives the number of stored entries.  Synchronous (the output size is
+ * data dependent).  d_work: at least b2w_csr_from_edges_work_bytes(n, m, directed) bytes of device scratch. */
+size_t b2w_csr_from_edges_work_bytes(uint32_t num_nodes, uint64_t num_edges, int directed);
+int b2w_csr_from_edges(int device, uint32_t num_nodes, uint64_t num_edges, const uint32_t* d_src,
+                       const uint32_t* d_dst, const double* d_weight, int directed, uint32_t* d_indptr,
+                       uint32_t* d_indices, float* d_data, uint64_t* h_nnz, void* d_work, size_t work_bytes,
+                       void* stream);
 
 /* ---- node2vec+ noise thresholds ----------------------------------------------------------
  * Replaces SparseRWGraph.get_noise_thresholds (rw/sparse_rw.py:22-35) and

@@ -22,7 +22,6 @@ FLAG_THREAD_PER_WALKER = 0x4
 FLAG_NO_UNWEIGHTED_KERNEL = 0x8
 FLAG_NO_TMA = 0x10
 FLAG_COOP = 0x20
-FLAG_L2_PERSIST = 0x40
 
 
 def FLAG_GROUP(n: int) -> int:
@@ -34,7 +33,7 @@ EXPORTS = [
     "b2w_version", "b2w_last_error", "b2w_device_count", "b2w_graph_csr_create", "b2w_graph_dense_create",
     "b2w_graph_info_get", "b2w_graph_destroy", "b2w_alias_build_work_bytes", "b2w_alias_build",
     "b2w_alias_build_first_order", "b2w_graph_set_alias", "b2w_walk_work_bytes", "b2w_walk", "b2w_walk_host",
-    "b2w_count_steps", "b2w_philox_selftest", "b2w_walk_kernel_name", "b2w_noise_thresholds",
+    "b2w_count_steps", "b2w_philox_selftest", "b2w_walk_kernel_name", "b2w_noise_thresholds", "b2w_csr_from_edges_work_bytes", "b2w_csr_from_edges",
 ]
 
 
@@ -85,6 +84,9 @@ def lib():
     L.b2w_walk_kernel_name.argtypes = [vp, i32, dbl, dbl, i32, u32]
     L.b2w_walk_kernel_name.restype = C.c_char_p
     L.b2w_noise_thresholds.argtypes = [vp, dbl, vp, vp]
+    L.b2w_csr_from_edges_work_bytes.argtypes = [u32, u64, i32]
+    L.b2w_csr_from_edges_work_bytes.restype = sz
+    L.b2w_csr_from_edges.argtypes = [i32, u32, u64, vp, vp, vp, i32, vp, vp, vp, C.POINTER(u64), vp, sz, vp]
     L.b2w_count_steps.argtypes = [vp, u64, u32, u64, vp, vp]
     L.b2w_philox_selftest.argtypes = [C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
     for name in EXPORTS:

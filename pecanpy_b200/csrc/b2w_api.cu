@@ -140,8 +140,6 @@ static int new_handle(int device, b2w_graph** out, b2w_graph** gp) {
   cudaError_t e = cudaGetDeviceProperties(&prop, device);
   if (e != cudaSuccess) { delete g; return b2w_cuda_fail(e, "cudaGetDeviceProperties"); }
   g->num_sms = prop.multiProcessorCount;
-  g->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
-  g->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
   g->pipe = new (std::nothrow) b2w_host_pipe();
   if (!g->pipe) { delete g; b2w_set_error("graph create: out of host memory"); return B2W_ERR_NOMEM; }
   *gp = g;

@@ -16,8 +16,6 @@ struct b2w_graph {
   uint32_t max_degree;
   uint32_t flags;
   int num_sms;
-  size_t l2_persist_max;   // cudaDeviceProp::persistingL2CacheMaxSize
-  size_t l2_window_max;    // cudaDeviceProp::accessPolicyMaxWindowSize
   // CSR (borrowed)
   const uint32_t* indptr;
   const uint32_t* indices;
