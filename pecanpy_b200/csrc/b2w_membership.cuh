@@ -109,28 +109,38 @@ __device__ __forceinline__ uint32_t lower_bound_eq(const uint32_t* __restrict__ 
 #undef B2W_LB_PROBE
 
 
-// Two independent searches in the same row, interleaved probe by probe: the dependent-load chain of a search
-// (k + 1 loads, each an L1/L2 round trip on a hub row) is what a multi-chunk membership step waits for, and two
-// chunks in flight halve the number of such chains per step.
-__device__ __forceinline__ void lower_bound_eq_x2(const uint32_t* __restrict__ row, const uint32_t n, const uint32_t x0,
-                                                  const uint32_t x1, const uint32_t k, uint32_t& lo0, bool& f0,
-                                                  uint32_t& lo1, bool& f1) {
+// N independent searches in the same row, interleaved probe by probe: the dependent-load chain of a search
+// (k + 1 loads, each an L1/L2 round trip on a hub row) is what a multi-chunk membership step waits for, and N
+// chunks in flight divide the number of such chains per step by N.
+template <int N>
+__device__ __forceinline__ void lower_bound_eq_xN(const uint32_t* __restrict__ row, const uint32_t n, const uint32_t (&x)[N],
+                                                  const uint32_t k, uint32_t (&lo)[N], bool (&found)[N]) {
   const uint32_t top = 1u << k;
   const uint32_t v = __ldg(row + (top - 1));
-  uint32_t ge0 = (v < x0) ? B2W_NONE : v, ge1 = (v < x1) ? B2W_NONE : v;
-  lo0 = (v < x0) ? n - top + 1 : 0u;
-  lo1 = (v < x1) ? n - top + 1 : 0u;
-  for (uint32_t S = top >> 1; S; S >>= 1) {
-    const uint32_t a = __ldg(row + (lo0 + S - 1u)), b = __ldg(row + (lo1 + S - 1u));
-    if (a < x0) lo0 += S; else ge0 = a;
-    if (b < x1) lo1 += S; else ge1 = b;
+  uint32_t ge[N];
+#pragma unroll
+  for (int t = 0; t < N; ++t) {
+    ge[t] = (v < x[t]) ? B2W_NONE : v;
+    lo[t] = (v < x[t]) ? n - top + 1 : 0u;
   }
-  f0 = ge0 == x0;
-  f1 = ge1 == x1;
+  for (uint32_t S = top >> 1; S; S >>= 1) {
+    uint32_t a[N];
+#pragma unroll
+    for (int t = 0; t < N; ++t) a[t] = __ldg(row + (lo[t] + S - 1u));
+#pragma unroll
+    for (int t = 0; t < N; ++t) { if (a[t] < x[t]) lo[t] += S; else ge[t] = a[t]; }
+  }
+#pragma unroll
+  for (int t = 0; t < N; ++t) found[t] = ge[t] == x[t];
 }
-// B2W_DUAL_CHUNKS: measured on BASELINE config #3, 32-lane groups: 1.92 -> 2.06 G steps/s.
-#ifndef B2W_DUAL_CHUNKS
-#define B2W_DUAL_CHUNKS 1
+// Chunks of G keys searched per iteration.  Measured (G steps/s): BASELINE config #3, 32-lane groups: 1 chunk 1.92,
+// 2 chunks 2.06 / 2.04, 3 chunks 2.03, 4 chunks 1.90;  config #2, 8-lane groups: 1 chunk 4.35, 2 chunks 4.62-4.70,
+// 3 chunks 5.21, 4 chunks 5.38 (a whole in-register word, 32 positions, in one iteration).
+#ifndef B2W_CHUNKS_WARP
+#define B2W_CHUNKS_WARP 2      /* 32-lane groups */
+#endif
+#ifndef B2W_CHUNKS_SUBWARP
+#define B2W_CHUNKS_SUBWARP 0   /* sub-warp groups: 0 = 32 / G (one bitmap word per iteration) */
 #endif
 
 
@@ -165,21 +175,28 @@ __device__ __forceinline__ uint32_t membership_bitmap(const Tile<G>& T, const ui
     // single-word row (the common case): the bitmap stays in a register -- no shared-memory store, no group
     // sync; the caller materialises it only if it has to replay
     uint32_t c0 = 0;
-    if (B2W_DUAL_CHUNKS != 0 && G < 32) {
-      for (; c0 + G < d; c0 += 2 * G) {                               // sub-warp groups: two chunks per iteration
-        const uint32_t k0 = c0 + T.tl, k1 = k0 + G;
-        const bool valid1 = k1 < d;
-        const uint32_t x0 = __ldg(crow + k0);
-        const uint32_t x1 = valid1 ? __ldg(crow + k1) : B2W_NONE;
-        uint32_t p0, p1;
-        bool f0, f1;
-        lower_bound_eq_x2(prow, pdeg, x0, x1, kp2, p0, f0, p1, f1);
-        const bool isprev0 = x0 == prev, isprev1 = valid1 && (x1 == prev);
-        kp = min(kp, __reduce_min_sync(T.mask, isprev0 ? k0 : (isprev1 ? k1 : B2W_NONE)));
-        const uint32_t bal0 = T.ballot(f0 && !isprev0);
-        const uint32_t bal1 = T.ballot(valid1 && f1 && !isprev1);
-        word0 |= (bal0 << c0) | (bal1 << (c0 + G));
-        m += __popc(bal0) + __popc(bal1);
+    if (G < 32) {
+      constexpr int N = B2W_CHUNKS_SUBWARP > 1 ? B2W_CHUNKS_SUBWARP : (32 / G > 1 ? 32 / G : 2);
+      for (; c0 + G < d; c0 += N * G) {                               // sub-warp groups: N chunks per iteration
+        uint32_t x[N], p[N], kk[N];
+        bool f[N], valid[N];
+#pragma unroll
+        for (int t = 0; t < N; ++t) {
+          kk[t] = c0 + t * G + T.tl;
+          valid[t] = kk[t] < d;
+          x[t] = valid[t] ? __ldg(crow + kk[t]) : B2W_NONE;
+        }
+        lower_bound_eq_xN<N>(prow, pdeg, x, kp2, p, f);
+        uint32_t kpl = B2W_NONE;
+#pragma unroll
+        for (int t = 0; t < N; ++t) {
+          const bool isprev = valid[t] && (x[t] == prev);
+          if (isprev) kpl = kk[t];
+          const uint32_t bal = T.ballot(valid[t] && f[t] && !isprev);
+          if (c0 + t * G < 32) word0 |= bal << (c0 + t * G);
+          m += __popc(bal);
+        }
+        kp = min(kp, __reduce_min_sync(T.mask, kpl));
       }
     }
     for (; c0 < d; c0 += G) {
@@ -197,24 +214,31 @@ __device__ __forceinline__ uint32_t membership_bitmap(const Tile<G>& T, const ui
     in_regs = true;
     return m;
   }
-  constexpr bool DUAL = (B2W_DUAL_CHUNKS != 0) && G == 32;
+  constexpr bool MULTI = (B2W_CHUNKS_WARP > 1) && G == 32;
+  constexpr int N = B2W_CHUNKS_WARP > 1 ? B2W_CHUNKS_WARP : 2;
   if (d <= 2 * 32 || fwd_cost <= rev_cost) {
     uint32_t c0 = 0;
-    if (DUAL) {
-      for (; c0 + G < d; c0 += 2 * G) {                               // two chunks of the row per iteration
-        const uint32_t k0 = c0 + T.tl, k1 = k0 + G;
-        const bool valid1 = k1 < d;
-        const uint32_t x0 = __ldg(crow + k0);
-        const uint32_t x1 = valid1 ? __ldg(crow + k1) : B2W_NONE;
-        uint32_t p0, p1;
-        bool f0, f1;
-        lower_bound_eq_x2(prow, pdeg, x0, x1, kp2, p0, f0, p1, f1);
-        const bool isprev0 = x0 == prev, isprev1 = valid1 && (x1 == prev);
-        kp = min(kp, __reduce_min_sync(T.mask, isprev0 ? k0 : (isprev1 ? k1 : B2W_NONE)));
-        const uint32_t bal0 = T.ballot(f0 && !isprev0);
-        const uint32_t bal1 = T.ballot(valid1 && f1 && !isprev1);
-        if (T.tl == 0) { bm[c0 >> 5] = bal0; bm[(c0 >> 5) + 1] = bal1; }
-        m += __popc(bal0) + __popc(bal1);
+    if (MULTI) {
+      for (; c0 + G < d; c0 += N * G) {                               // N chunks of the row per iteration
+        uint32_t x[N], p[N], kk[N];
+        bool f[N], valid[N];
+#pragma unroll
+        for (int t = 0; t < N; ++t) {
+          kk[t] = c0 + t * G + T.tl;
+          valid[t] = kk[t] < d;
+          x[t] = valid[t] ? __ldg(crow + kk[t]) : B2W_NONE;
+        }
+        lower_bound_eq_xN<N>(prow, pdeg, x, kp2, p, f);
+        uint32_t kpl = B2W_NONE;
+#pragma unroll
+        for (int t = 0; t < N; ++t) {
+          const bool isprev = valid[t] && (x[t] == prev);
+          if (isprev) kpl = kk[t];
+          const uint32_t bal = T.ballot(valid[t] && f[t] && !isprev);
+          if (T.tl == 0 && c0 + t * G < d) bm[(c0 >> 5) + t] = bal;
+          m += __popc(bal);
+        }
+        kp = min(kp, __reduce_min_sync(T.mask, kpl));
       }
     }
     for (; c0 < d; c0 += G) {
@@ -237,22 +261,22 @@ __device__ __forceinline__ uint32_t membership_bitmap(const Tile<G>& T, const ui
     const uint32_t nkeys = pdeg + 1;
     uint32_t mloc = 0, kploc = B2W_NONE;
     uint32_t c0 = 0;
-    if (DUAL) {
-      for (; c0 + G < nkeys; c0 += 2 * G) {                           // two chunks of keys per iteration
-        const uint32_t i0 = c0 + T.tl, i1 = i0 + G;
-        const bool valid1 = i1 < nkeys;
-        const uint32_t y0 = i0 < pdeg ? __ldg(prow + i0) : prev;
-        const uint32_t y1 = valid1 ? (i1 < pdeg ? __ldg(prow + i1) : prev) : B2W_NONE;
-        uint32_t p0, p1;
-        bool f0, f1;
-        lower_bound_eq_x2(crow, d, y0, y1, kd2, p0, f0, p1, f1);
-        if (f0) {
-          if (i0 == pdeg) kploc = p0;
-          else if (y0 != prev) { atomicOr(&bm[p0 >> 5], 1u << (p0 & 31)); ++mloc; }
+    if (MULTI) {
+      for (; c0 + G < nkeys; c0 += N * G) {                           // N chunks of keys per iteration
+        uint32_t y[N], p[N], ii[N];
+        bool f[N];
+#pragma unroll
+        for (int t = 0; t < N; ++t) {
+          ii[t] = c0 + t * G + T.tl;
+          y[t] = ii[t] < nkeys ? (ii[t] < pdeg ? __ldg(prow + ii[t]) : prev) : B2W_NONE;
         }
-        if (valid1 && f1) {
-          if (i1 == pdeg) kploc = p1;
-          else if (y1 != prev) { atomicOr(&bm[p1 >> 5], 1u << (p1 & 31)); ++mloc; }
+        lower_bound_eq_xN<N>(crow, d, y, kd2, p, f);
+#pragma unroll
+        for (int t = 0; t < N; ++t) {
+          if (ii[t] < nkeys && f[t]) {
+            if (ii[t] == pdeg) kploc = p[t];
+            else if (y[t] != prev) { atomicOr(&bm[p[t] >> 5], 1u << (p[t] & 31)); ++mloc; }
+          }
         }
       }
     }
