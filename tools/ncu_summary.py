@@ -37,6 +37,10 @@ def main():
         stalls = [(float(d[h]), h) for h in hdr if "warp_issue_stalled" in h and h.endswith("_per_warp_active.pct") and d[h]]
         for v, h in sorted(stalls, reverse=True)[:8]:
             lines.append(f"  stall {h.split('issue_stalled_')[1].replace('_per_warp_active.pct', ''):40s} {v:8.2f} % of active warps")
+        # newer ncu: average number of warps per scheduler in each stall state, per issued instruction
+        ratios = [(float(d[h]), h) for h in hdr if "average_warps_issue_stalled" in h and h.endswith("_per_issue_active.ratio") and d[h]]
+        for v, h in sorted(ratios, reverse=True)[:8]:
+            lines.append(f"  stall {h.split('issue_stalled_')[1].replace('_per_issue_active.ratio', ''):40s} {v:8.2f} warps per issue")
         try:
             t = float(d["gpu__time_duration.sum"])
             tu = u["gpu__time_duration.sum"]
