@@ -117,6 +117,21 @@ int b2w_graph_dense_create(int device, uint32_t num_nodes, const double* d_data,
 int b2w_graph_info_get(const b2w_graph* g, b2w_graph_info* out);
 void b2w_graph_destroy(b2w_graph* g);
 
+/* ---- ingest: `.edg` text -> integer endpoints (HOST code, no device work) ---------------------
+ * Replaces the per-line Python of AdjlstGraph.read / _read_edge_line / add_edge / add_node (graph.py:160-180,
+ * 217-236, 258-305) with the same conventions: terms = line.strip().split(delimiter), ids stripped, weighted files
+ * need exactly three columns, lines with weight <= 0 are ignored and do not register their ids, node index = order
+ * of first appearance (id1 before id2).  b2w_edgelist_parse reads the whole file and reports the sizes;
+ * b2w_edgelist_fetch copies endpoints / weights (file order) and the ids (NUL separated, node order) into
+ * caller buffers of those sizes; b2w_edgelist_free releases the handle.  Files containing non-ASCII bytes return
+ * B2W_ERR_UNSUPPORTED (Python's strip() is Unicode aware; fall back to it).  Malformed lines: B2W_ERR_GRAPH. */
+typedef struct b2w_edgelist b2w_edgelist; /* opaque */
+int b2w_edgelist_parse(const char* path, int weighted, const char* delimiter, b2w_edgelist** out,
+                       uint64_t* num_edges, uint32_t* num_nodes, uint64_t* names_bytes, uint64_t* num_dropped);
+int b2w_edgelist_fetch(const b2w_edgelist* e, uint32_t* h_src, uint32_t* h_dst, double* h_weight, char* h_names,
+                       uint64_t* h_dropped_lines /* room for 20 */, uint32_t* n_dropped_lines);
+void b2w_edgelist_free(b2w_edgelist* e);
+
 /* ---- ingest: edge list -> CSR ------------------------------------------------------------
  * Replaces the dict-of-dicts build of AdjlstGraph.read / add_edge (graph.py:160-305) + to_csr (graph.py:308-341)
  * once the text has been parsed into integer endpoints (node numbering by first appearance and the dropping of

@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("B2W_LIBRARY") or os.path.join(_HERE, "lib", "libb2w.so")
 
 OK = 0
+ERR_UNSUPPORTED = -4
 MODE_SPARSE_OTF, MODE_PRECOMP, MODE_DENSE_OTF, MODE_FIRST_ORDER_UNWEIGHTED, MODE_PRECOMP_FIRST_ORDER = range(5)
 RNG_PHILOX, RNG_FEED = 0, 1
 FLAG_FORCE_EXACT_REPLAY = 0x1
@@ -34,6 +35,7 @@ EXPORTS = [
     "b2w_graph_info_get", "b2w_graph_destroy", "b2w_alias_build_work_bytes", "b2w_alias_build",
     "b2w_alias_build_first_order", "b2w_graph_set_alias", "b2w_walk_work_bytes", "b2w_walk", "b2w_walk_host",
     "b2w_count_steps", "b2w_philox_selftest", "b2w_walk_kernel_name", "b2w_noise_thresholds", "b2w_csr_from_edges_work_bytes", "b2w_csr_from_edges",
+    "b2w_edgelist_parse", "b2w_edgelist_fetch", "b2w_edgelist_free",
 ]
 
 
@@ -87,6 +89,11 @@ def lib():
     L.b2w_csr_from_edges_work_bytes.argtypes = [u32, u64, i32]
     L.b2w_csr_from_edges_work_bytes.restype = sz
     L.b2w_csr_from_edges.argtypes = [i32, u32, u64, vp, vp, vp, i32, vp, vp, vp, C.POINTER(u64), vp, sz, vp]
+    L.b2w_edgelist_parse.argtypes = [C.c_char_p, i32, C.c_char_p, C.POINTER(vp), C.POINTER(u64), C.POINTER(u32),
+                                     C.POINTER(u64), C.POINTER(u64)]
+    L.b2w_edgelist_fetch.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(u32)]
+    L.b2w_edgelist_free.argtypes = [vp]
+    L.b2w_edgelist_free.restype = None
     L.b2w_count_steps.argtypes = [vp, u64, u32, u64, vp, vp]
     L.b2w_philox_selftest.argtypes = [C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
     for name in EXPORTS:

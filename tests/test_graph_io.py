@@ -88,3 +88,93 @@ def test_npz_round_trip_and_from_mat(tmp_path):
     assert np.all(u.data == 1.0)
     d = DenseGraph.from_mat(mat, ["a", "b", "c"])
     assert d.num_edges == 4 and d.nonzero.dtype == bool
+
+
+# ------------------------------------------------------------------------------------------ native parser
+def _reference_read_lines(path, weighted, delimiter="\t"):
+    """AdjlstGraph.read restated line by line (graph.py:160-193, 217-236, 258-305): ids, endpoints, weights in
+    file order; lines with weight <= 0 are ignored and do not register their ids."""
+    ids, src, dst, w = {}, [], [], []
+    with open(path, encoding="utf-8") as f:
+        for line in f:
+            if not line.strip():
+                continue
+            terms = line.strip().split(delimiter)
+            id1, id2 = terms[0].strip(), terms[1].strip()
+            weight = 1.0
+            if weighted:
+                if len(terms) != 3:
+                    raise ValueError("Expecting three columns")
+                weight = float(terms[-1])
+            if weight <= 0:
+                continue
+            for x in (id1, id2):
+                if x not in ids:
+                    ids[x] = len(ids)
+            src.append(ids[id1]); dst.append(ids[id2]); w.append(weight)
+    return list(ids), np.array(src, np.int64), np.array(dst, np.int64), np.array(w, np.float64)
+
+
+def _same_parse(a, b):
+    return a[0] == b[0] and all(np.array_equal(x, y) for x, y in zip(a[1:], b[1:]))
+
+
+@pytest.mark.parametrize("weighted", [False, True])
+def test_native_parser_equals_reference_conventions(tmp_path, weighted):
+    import warnings
+    from pecanpy_b200.graph import _parse_edge_list_native, _parse_edge_list_python
+    rng = np.random.default_rng(5)
+    path = tmp_path / "g.edg"
+    weights = ["0.5", "1.5", "2", "-1.0", "0", "1e-3", "3.25E+2", " 7.125 ", ".5", "5.", "+4", "inf", "0.1234567890123456789"]
+    with open(path, "w", newline="") as f:
+        for i in range(2000):
+            a, b = rng.integers(0, 60, size=2)
+            ida = f" n{a} " if i % 7 == 0 else f"n{a}"                 # ids are stripped
+            eol = "\r\n" if i % 5 == 0 else "\n"                       # strip() eats the CR
+            if weighted:
+                f.write(f"{ida}\tn{b}\t{weights[i % len(weights)]}{eol}")
+            else:
+                extra = "\tignored" if i % 11 == 0 else ""            # extra columns are ignored when unweighted
+                f.write(f"{ida}\tn{b}{extra}{eol}")
+            if i % 97 == 0:
+                f.write("\n")                                          # blank lines are skipped
+        f.write("last\tline" + ("\t1.0" if weighted else ""))          # no trailing newline
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        nat = _parse_edge_list_native(str(path), weighted, "\t")
+        py = _parse_edge_list_python(str(path), weighted, "\t")
+    assert nat is not None, "libb2w.so must be built for this test"
+    ref = _reference_read_lines(str(path), weighted)
+    assert _same_parse(nat, ref) and _same_parse(py, ref)
+
+
+def test_native_parser_other_delimiter_errors_and_unicode_fallback(tmp_path):
+    import warnings
+    from pecanpy_b200.graph import SparseGraph, _parse_edge_list_native, _parse_edge_list_python
+    p = tmp_path / "c.edg"
+    p.write_text("a, b, 1.5\nb,c,2\nc , a,0.25\n")
+    nat = _parse_edge_list_native(str(p), True, ",")
+    assert _same_parse(nat, _reference_read_lines(str(p), True, ","))
+    assert nat[0] == ["a", "b", "c"]
+    bad = tmp_path / "bad.edg"
+    bad.write_text("a\tb\n")
+    with pytest.raises(ValueError, match="three columns"):
+        _parse_edge_list_native(str(bad), True, "\t")
+    bad.write_text("a\tb\tx1\n")
+    with pytest.raises(ValueError, match="float"):
+        _parse_edge_list_native(str(bad), True, "\t")
+    bad.write_text("lonely\n")
+    with pytest.raises(ValueError):
+        _parse_edge_list_native(str(bad), False, "\t")
+    uni = tmp_path / "u.edg"
+    uni.write_text("café\tnaïve\n x \tcafé\n", encoding="utf-8")
+    assert _parse_edge_list_native(str(uni), False, "\t") is None      # refused: Python's strip() is Unicode aware
+    g = SparseGraph()
+    g.read_edg(str(uni), weighted=False, directed=False)                # falls back transparently
+    assert g.nodes == ["café", "naïve", "x"]
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        drop = tmp_path / "d.edg"
+        drop.write_text("a\tb\t-1\nb\tc\t2\n")
+        names, src, dst, w = _parse_edge_list_native(str(drop), True, "\t")
+    assert names == ["b", "c"] and len(rec) == 1 and "Non-positive" in str(rec[0].message)
