@@ -13,16 +13,16 @@
 //            O(deg(prev) log deg(cur)) words of the hub row -- this is what makes power-law hubs
 //            cheap).  T groups of G lanes (G = 8/16/32) each own one walker, so a warp keeps
 //            32/G independent gather chains in flight.
-//   phase 2  normaliser S: the host verified that 1, w_out, w_ret are multiples of one power of two g
-//            and max_degree * max(w) < 2^24 g, so NO f32 partial sum can round and the reference's
-//            sequential f32 sum equals the exact count-weighted total.  probs take three values
-//            pa = fdiv(w_in,S), po = fdiv(w_out,S), pp = fdiv(w_ret,S)  (exact f32 quotients).
-//            The reference's cdf_k (sequential f32 cumsum, numba/np/arraymath.py:384-405) obeys
-//            |cdf_k - T_k| <= gamma_k T_k with T_k = n_in(k) pa + n_out(k) po + [pos(prev)<=k] pp
-//            (exact, f64 from counts).  Popcount prefix over the bitmap words locates the first
-//            word, then the first position k, with T_k (1 + e_k) >= u; if also T_k (1 - e_k) >= u the
-//            choice is proven (e_k = (k+2) 1.01 2^-24).  Otherwise the group replays the f32
-//            recurrence exactly from the bitmap (no memory traffic).
+//   phase 2  normaliser: the host verified that 1, w_out, w_ret are multiples of one power of two g and
+//            (max_degree + 1) * max(w) < 2^24 g, so NO f32 partial sum can round and the reference's sequential
+//            f32 sum S equals the exact count-weighted total.  In units of g everything is a small integer:
+//            W_k = exact un-normalised prefix up to position k, W_d the total (S = W_d g).
+//   phase 3  filter: the reference's cdf_k (sequential f32 cumsum of fdiv(w_i, S), numba/np/arraymath.py:384-405)
+//            equals (W_k / W_d)(1 + t) with |t| <= e_k = 1.02 (k + 3) 2^-24.  Popcount prefix over the bitmap words
+//            locates the first word, then the first position k, with W_k >= u W_d (1 - e); if also
+//            W_k >= u W_d (1 + e + 2 e^2) the choice is proven.  Otherwise (~1 % of the steps on a power-law
+//            graph) the group forms the three f32 quotients and replays the f32 recurrence exactly from the
+//            bitmap (no memory traffic).
 // Bit-exact with the generic kernels and the oracle for every (cur, prev, u); dispatched only when
 // the exactness precondition holds (power-of-two-like p, q), else the generic stream kernel runs.
 //
@@ -452,7 +452,8 @@ int pick_group(const b2w_graph* g, uint32_t flags) {
   if (forced == 8 || forced == 16 || forced == 32) return (int)forced;
   double avg = g->n ? (double)g->nnz / g->n : 0.0;
   // measured (B200): 8 lanes per walker win on flat low-degree graphs (ER, deg 20: 3.72 / 3.44 / 2.97 G steps/s
-  // for 8 / 16 / 32 lanes), 32 lanes win as soon as there are hub rows (power law: 1.77 vs 1.39 for 16)
+  // for 8 / 16 / 32 lanes with the first-session kernel; 5.38 / 4.31 for 8 / 16 with the interleaved searches),
+  // 32 lanes win as soon as there are hub rows (power law: 1.77 vs 1.39 for 16)
   return (avg <= 32.0 && (double)g->max_degree <= 8.0 * avg + 16.0) ? 8 : 32;
 }
 
