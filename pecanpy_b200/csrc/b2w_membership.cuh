@@ -139,6 +139,10 @@ __device__ __forceinline__ void lower_bound_eq_xN(const uint32_t* __restrict__ r
 #ifndef B2W_CHUNKS_WARP
 #define B2W_CHUNKS_WARP 2      /* 32-lane groups */
 #endif
+#ifndef B2W_SUBWARP_REDUX
+#define B2W_SUBWARP_REDUX 0   /* sub-warp groups, rows <= 32: assemble the bitmap word with one REDUX.OR.  Parity-green on
+                                  the B200 (uw-g8 / uw-g16 suites, 88 tests) but NOT yet timed -- off until measured */
+#endif
 #ifndef B2W_CHUNKS_SUBWARP
 #define B2W_CHUNKS_SUBWARP 0   /* sub-warp groups: 0 = 32 / G (one bitmap word per iteration) */
 #endif
@@ -175,6 +179,33 @@ __device__ __forceinline__ uint32_t membership_bitmap(const Tile<G>& T, const ui
     // single-word row (the common case): the bitmap stays in a register -- no shared-memory store, no group
     // sync; the caller materialises it only if it has to replay
     uint32_t c0 = 0;
+#if B2W_SUBWARP_REDUX
+    if (G < 32) {
+      // the whole word in one go: every lane searches its 32 / G positions, builds its own bits of the word and one
+      // REDUX.OR assembles it (instead of one ballot + shift + popcount per chunk)
+      constexpr int NW = 32 / G;
+      uint32_t x[NW], p[NW], kk[NW];
+      bool f[NW];
+#pragma unroll
+      for (int t = 0; t < NW; ++t) {
+        kk[t] = t * G + T.tl;
+        x[t] = kk[t] < d ? __ldg(crow + kk[t]) : B2W_NONE;
+      }
+      lower_bound_eq_xN<NW>(prow, pdeg, x, kp2, p, f);
+      uint32_t mine = 0u, kpl = B2W_NONE;
+#pragma unroll
+      for (int t = 0; t < NW; ++t) {
+        const bool valid = kk[t] < d;
+        const bool isprev = valid && (x[t] == prev);
+        if (isprev) kpl = kk[t];
+        if (valid && f[t] && !isprev) mine |= 1u << kk[t];
+      }
+      word0 = __reduce_or_sync(T.mask, mine);
+      kp = __reduce_min_sync(T.mask, kpl);
+      in_regs = true;
+      return __popc(word0);
+    }
+#endif
     if (G < 32) {
       constexpr int N = B2W_CHUNKS_SUBWARP > 1 ? B2W_CHUNKS_SUBWARP : (32 / G > 1 ? 32 / G : 2);
       for (; c0 + G < d; c0 += N * G) {                               // sub-warp groups: N chunks per iteration
