@@ -337,7 +337,13 @@ extern "C" int b2w_walk_host(const b2w_graph* g, int mode, double p, double q, i
   if (n_rows == 0) return B2W_OK;
   if (!h_start || !h_out) { b2w_set_error("b2w_walk_host: null start/out"); return B2W_ERR_INVALID; }
   B2W_CUDA(cudaSetDevice(g->device));
-  if (batch_rows == 0) batch_rows = 1u << 19;
+  if (batch_rows == 0) {
+    // default: ~8 batches so that H2D / kernel / D2H of neighbouring batches overlap even for small jobs (with two
+    // batches the last D2H is fully exposed), between 64K and 512K rows (config #3: 20 batches of 512K rows)
+    batch_rows = ((n_rows + 7) / 8 + 1023) & ~(uint64_t)1023;
+    if (batch_rows < (1u << 16)) batch_rows = 1u << 16;
+    if (batch_rows > (1u << 19)) batch_rows = 1u << 19;
+  }
   if (batch_rows > n_rows) batch_rows = n_rows;
   const uint64_t ld = (uint64_t)L + 2;
   const size_t wb = b2w_walk_work_bytes(g, mode);
