@@ -75,6 +75,8 @@ def _parse_edge_list_native(path: str, weighted: bool, delimiter: str):
         lib = capi.lib()
     except (ImportError, OSError):
         return None
+    with open(path, "rb"):                # same exceptions as the reference's open() for a missing / unreadable file
+        pass
     h = C.c_void_p(None)
     m, n, nb, nd = C.c_uint64(0), C.c_uint32(0), C.c_uint64(0), C.c_uint64(0)
     rc = lib.b2w_edgelist_parse(os.fsencode(path), int(bool(weighted)), delimiter.encode("utf-8"), C.byref(h), C.byref(m),
