@@ -139,6 +139,10 @@ __device__ __forceinline__ void lower_bound_eq_xN(const uint32_t* __restrict__ r
 #ifndef B2W_CHUNKS_WARP
 #define B2W_CHUNKS_WARP 2      /* 32-lane groups */
 #endif
+#ifndef B2W_INREG_MEMBERSHIP
+#define B2W_INREG_MEMBERSHIP 0 /* 32-lane groups, both rows <= 32 entries: search row(prev) in registers with shuffles.
+                                  Written at the end of round 1 from the cost model; NOT yet run on a GPU -- off */
+#endif
 #ifndef B2W_SUBWARP_REDUX
 #define B2W_SUBWARP_REDUX 0   /* sub-warp groups, rows <= 32: assemble the bitmap word with one REDUX.OR.  Parity-green on
                                   the B200 (uw-g8 / uw-g16 suites, 88 tests) but NOT yet timed -- off until measured */
@@ -179,6 +183,29 @@ __device__ __forceinline__ uint32_t membership_bitmap(const Tile<G>& T, const ui
     // single-word row (the common case): the bitmap stays in a register -- no shared-memory store, no group
     // sync; the caller materialises it only if it has to replay
     uint32_t c0 = 0;
+#if B2W_INREG_MEMBERSHIP
+    if (G == 32 && pdeg <= 32) {
+      // both rows fit one register per lane: row(prev) is loaded once (coalesced) and searched with shuffles -- one
+      // memory round trip instead of a chain of k + 1 dependent loads (31 % of the steps of config #3,
+      // profiles/r1_costmodel_config3.txt).  Padding with B2W_NONE keeps the 32 values sorted.
+      const uint32_t pv = (uint32_t)T.tl < pdeg ? __ldg(prow + T.tl) : B2W_NONE;
+      const uint32_t k = T.tl;
+      const bool valid = k < d;
+      const uint32_t x = valid ? __ldg(crow + k) : B2W_NONE;
+      uint32_t base = 0;
+#pragma unroll
+      for (uint32_t half = 16; half; half >>= 1) {                    // lower_bound over 32 register-resident values
+        const uint32_t v = __shfl_sync(B2W_FULL, pv, (int)(base + half - 1));
+        if (v < x) base += half;
+      }
+      const bool found = __shfl_sync(B2W_FULL, pv, (int)base) == x;   // (idle lanes match the padding: masked below)
+      const bool isprev = valid && (x == prev);
+      kp = __reduce_min_sync(T.mask, isprev ? k : B2W_NONE);
+      word0 = T.ballot(valid && found && !isprev);
+      in_regs = true;
+      return __popc(word0);
+    }
+#endif
 #if B2W_SUBWARP_REDUX
     if (G < 32) {
       // the whole word in one go: every lane searches its 32 / G positions, builds its own bits of the word and one

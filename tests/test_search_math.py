@@ -48,3 +48,25 @@ def test_invalid_lane_key_walks_to_the_end():
     row = [3, 9, 27, 81]
     pos, found = lower_bound_eq(row, NONE)
     assert pos == 4 and found
+
+
+def inreg_found(prow, x):
+    """B2W_INREG_MEMBERSHIP (off by default): row(prev) padded to 32 register lanes with the sentinel, five
+    shuffle-probes of a power-of-two lower_bound, then one equality probe."""
+    pv = list(prow) + [NONE] * (32 - len(prow))
+    base, half = 0, 16
+    while half:
+        if pv[base + half - 1] < x:
+            base += half
+        half >>= 1
+    assert 0 <= base < 32
+    return pv[base] == x
+
+
+def test_in_register_membership_is_exact_for_rows_up_to_32():
+    rng = np.random.default_rng(1)
+    for n in range(1, 33):
+        for _ in range(20):
+            row = sorted(int(v) for v in rng.choice(200, size=n, replace=False))
+            for x in range(0, 201):
+                assert inreg_found(row, x) == (x in row), (row, x)
