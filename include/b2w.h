@@ -69,6 +69,7 @@ typedef enum {
 #define B2W_FLAG_NO_UNWEIGHTED_KERNEL 0x8u /* SparseOTF: always use the generic (weight-streaming) kernel */
 #define B2W_FLAG_NO_TMA 0x10u /* DenseOTF: per-lane vector loads instead of cp.async.bulk staging */
 #define B2W_FLAG_COOP 0x20u /* unweighted SparseOTF, G < 32: warp-cooperative state-machine kernel (long rows by all 32 lanes) */
+#define B2W_FLAG_NO_EDGE_INDEX 0x40u /* unweighted SparseOTF / PreComp: ignore an attached edge index (on-the-fly membership kernels) */
 #define B2W_FLAG_GROUP(n) (((uint32_t)(n) & 0xFFu) << 8) /* tuning: lanes per walker (8/16/32), 0 = auto */
 
 typedef struct b2w_graph b2w_graph; /* opaque */
@@ -84,6 +85,7 @@ typedef struct {
 #define B2W_GRAPH_DENSE 0x2u
 #define B2W_GRAPH_UNWEIGHTED 0x4u /* every stored weight == 1.0f */
 #define B2W_GRAPH_HAS_ALIAS 0x8u
+#define B2W_GRAPH_HAS_EDGE_INDEX 0x10u
 
 typedef struct {
   uint64_t steps;            /* walk steps taken (sum of effective_length - 1)           */
@@ -177,6 +179,35 @@ int b2w_alias_build_first_order(const b2w_graph* g, uint32_t* d_alias_j, float* 
  * For B2W_MODE_PRECOMP_FIRST_ORDER pass d_alias_indptr = NULL. */
 int b2w_graph_set_alias(b2w_graph* g, const uint64_t* d_alias_indptr, const uint32_t* d_alias_j,
                         const float* d_alias_q);
+
+/* ---- per-edge index ----------------------------------------------------------------------
+ * What a 2nd-order step along a stored edge e = (prev -> cur) needs and the reference recomputes every time the
+ * step is taken: the position of prev in row(cur) (rw/sparse_rw.py:87; np.searchsorted in pecanpy.py:429), the
+ * positions in row(cur) of the common neighbours of cur and prev (isnotin, rw/sparse_rw.py:142-230), deg(cur) and
+ * cur itself -- a function of the EDGE, so it is computed once per graph (one sorted-row intersection per edge, the
+ * work of one walk step per edge) and kept in HBM:
+ *     d_rec  b2w_edge_rec[nnz + 1]   16 bytes per stored edge (+ one pad record)
+ *     d_tri  uint32[tri_words]       per edge with common neighbours: their count m, then m ascending positions
+ * With the index attached, unweighted SparseOTF walks run a lane-per-walker kernel whose step is O(1 + log m)
+ * arithmetic on one record (no row is read), and PreComp steps need no search in row(cur).  Walks are bit-identical
+ * with and without it.  Two phases because the list size is data dependent:
+ *   b2w_edge_index_prepare  writes the records, counts the lists; *h_tri_words = words to allocate for d_tri
+ *                           (synchronous; B2W_ERR_UNSUPPORTED when they do not fit 32-bit offsets);
+ *   b2w_edge_index_finish   fills the lists and attaches the index (borrowed until detached / destroy; synchronous).
+ * d_work: at least b2w_edge_index_work_bytes(g) bytes, the SAME untouched buffer in both calls.  d_rec must be
+ * 16-byte aligned.  b2w_graph_set_edge_index(g, NULL, NULL, 0) detaches. */
+typedef struct {
+  uint32_t nxt; /* indices[e]: the node the edge leads to                                                  */
+  uint32_t kpf; /* bits 0..29 lower_bound(row(nxt), src(e)); bit 30: src(e) is NOT in row(nxt); bit 31: list */
+  uint32_t tri; /* offset of the edge's list in d_tri (valid when bit 31 of kpf is set)                    */
+  uint32_t deg; /* deg(nxt)                                                                                */
+} b2w_edge_rec;
+size_t b2w_edge_index_work_bytes(const b2w_graph* g);
+int b2w_edge_index_prepare(const b2w_graph* g, void* d_rec, void* d_work, size_t work_bytes, uint64_t* h_tri_words,
+                           void* stream);
+int b2w_edge_index_finish(b2w_graph* g, void* d_rec, uint32_t* d_tri, uint64_t tri_words, void* d_work,
+                          size_t work_bytes, void* stream);
+int b2w_graph_set_edge_index(b2w_graph* g, const void* d_rec, const uint32_t* d_tri, uint64_t tri_words);
 
 /* ---- the walk kernel -------------------------------------------------------------------
  * Replaces Base._random_walks (pecanpy.py:164-210) together with the move_forward closure of

@@ -23,12 +23,13 @@ FLAG_THREAD_PER_WALKER = 0x4
 FLAG_NO_UNWEIGHTED_KERNEL = 0x8
 FLAG_NO_TMA = 0x10
 FLAG_COOP = 0x20
+FLAG_NO_EDGE_INDEX = 0x40
 
 
 def FLAG_GROUP(n: int) -> int:
     return (n & 0xFF) << 8
 
-GRAPH_CSR, GRAPH_DENSE, GRAPH_UNWEIGHTED, GRAPH_HAS_ALIAS = 0x1, 0x2, 0x4, 0x8
+GRAPH_CSR, GRAPH_DENSE, GRAPH_UNWEIGHTED, GRAPH_HAS_ALIAS, GRAPH_HAS_EDGE_INDEX = 0x1, 0x2, 0x4, 0x8, 0x10
 
 EXPORTS = [
     "b2w_version", "b2w_last_error", "b2w_device_count", "b2w_graph_csr_create", "b2w_graph_dense_create",
@@ -36,6 +37,7 @@ EXPORTS = [
     "b2w_alias_build_first_order", "b2w_graph_set_alias", "b2w_walk_work_bytes", "b2w_walk", "b2w_walk_host",
     "b2w_count_steps", "b2w_philox_selftest", "b2w_walk_kernel_name", "b2w_noise_thresholds", "b2w_csr_from_edges_work_bytes", "b2w_csr_from_edges",
     "b2w_edgelist_parse", "b2w_edgelist_fetch", "b2w_edgelist_free",
+    "b2w_edge_index_work_bytes", "b2w_edge_index_prepare", "b2w_edge_index_finish", "b2w_graph_set_edge_index",
 ]
 
 
@@ -94,6 +96,11 @@ def lib():
     L.b2w_edgelist_fetch.argtypes = [vp, vp, vp, vp, vp, vp, C.POINTER(u32)]
     L.b2w_edgelist_free.argtypes = [vp]
     L.b2w_edgelist_free.restype = None
+    L.b2w_edge_index_work_bytes.argtypes = [vp]
+    L.b2w_edge_index_work_bytes.restype = sz
+    L.b2w_edge_index_prepare.argtypes = [vp, vp, vp, sz, C.POINTER(u64), vp]
+    L.b2w_edge_index_finish.argtypes = [vp, vp, vp, u64, vp, sz, vp]
+    L.b2w_graph_set_edge_index.argtypes = [vp, vp, vp, u64]
     L.b2w_count_steps.argtypes = [vp, u64, u32, u64, vp, vp]
     L.b2w_philox_selftest.argtypes = [C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
     for name in EXPORTS:

@@ -308,7 +308,12 @@ extern "C" int b2w_walk(const b2w_graph* g, int mode, double p, double q, int ex
   if (dense) return b2w_launch_dense(g, ext, P, s);
   if (warp_kernel) {
     // unweighted graphs with exactly representable biases: the membership-bitmap kernel
-    if (!ext && !(flags & B2W_FLAG_NO_UNWEIGHTED_KERNEL) && b2w_uw_eligible(g, p, q)) return b2w_launch_uw(g, P, s);
+    if (!ext && !(flags & B2W_FLAG_NO_UNWEIGHTED_KERNEL) && b2w_uw_eligible(g, p, q)) {
+      // with the per-edge index: closed-form steps, one lane per walker (b2w_walk_edge.cu)
+      if ((g->flags & B2W_GRAPH_HAS_EDGE_INDEX) && !(flags & (B2W_FLAG_NO_EDGE_INDEX | B2W_FLAG_COOP)) && !((flags >> 8) & 0xFF))
+        return b2w_launch_uw_edge(g, P, s);
+      return b2w_launch_uw(g, P, s);
+    }
     return b2w_launch_sparse_warp(g, P, s);
   }
   return b2w_launch_thread_walk(g, mode, ext, P, s);
@@ -323,7 +328,11 @@ extern "C" const char* b2w_walk_kernel_name(const b2w_graph* g, int mode, double
     case B2W_MODE_PRECOMP_FIRST_ORDER: return "walk_thread_kernel<PRECOMP_FIRST_ORDER>";
     case B2W_MODE_SPARSE_OTF:
       if (flags & B2W_FLAG_THREAD_PER_WALKER) return "walk_thread_kernel<SPARSE_OTF>";
-      if (!extend && !(flags & B2W_FLAG_NO_UNWEIGHTED_KERNEL) && b2w_uw_eligible(g, p, q)) return "walk_uw_kernel";
+      if (!extend && !(flags & B2W_FLAG_NO_UNWEIGHTED_KERNEL) && b2w_uw_eligible(g, p, q)) {
+        if ((g->flags & B2W_GRAPH_HAS_EDGE_INDEX) && !(flags & (B2W_FLAG_NO_EDGE_INDEX | B2W_FLAG_COOP)) && !((flags >> 8) & 0xFF))
+          return "walk_uw_edge_kernel";
+        return "walk_uw_kernel";
+      }
       return "walk_sparse_warp_kernel";
   }
   return "";

@@ -27,6 +27,10 @@ struct b2w_graph {
   const uint64_t* alias_indptr;
   const uint32_t* alias_j;
   const float* alias_q;
+  // per-edge index (borrowed; b2w_edge_index.cu)
+  const void* edge_rec;
+  const uint32_t* edge_tri;
+  uint64_t edge_tri_words;
   // staging buffers / streams of b2w_walk_host (lazily allocated, guarded by their own mutex)
   b2w_host_pipe* pipe;
 };
@@ -156,4 +160,6 @@ size_t b2w_sparse_warp_work_bytes(const b2w_graph* g);
 bool b2w_uw_eligible(const b2w_graph* g, double p, double q);
 size_t b2w_uw_work_bytes(const b2w_graph* g);
 int b2w_launch_uw(const b2w_graph* g, const WalkParams& P, cudaStream_t s);
+int b2w_launch_uw_edge(const b2w_graph* g, const WalkParams& P, cudaStream_t s);
+bool b2w_uw_grid(const b2w_graph* g, double p, double q, int* grid_exp);
 uint32_t b2w_sparse_warp_total_warps(const b2w_graph* g);

@@ -1,0 +1,241 @@
+// b2w_walk_edge.cu -- SparseOTF node2vec on UNWEIGHTED graphs through the per-edge index: one lane per walker.
+//
+// On an unweighted graph every biased weight of a step is one of  w_in = 1, w_out = f32(1/q), w_ret = f32(1/p)
+// (rw/sparse_rw.py:86-87), so the transition distribution of a step taken from `cur` after arriving over the edge
+// e = (prev -> cur) is fully described by  deg(cur),  the position kp of prev in row(cur)  and the sorted positions
+// p_0 < ... < p_{m-1} of the common neighbours -- which is what the edge index holds for e (b2w_edge_index.cu).
+// In integer units of the common weight grid g (host-verified: no f32 partial sum can round, b2w_walk_uw.cu) the
+// exact un-normalised prefix is
+//     W(k) = (k + 1) a_out + #{p_i <= k} (a_in - a_out) + [kp <= k] (a_ret - a_out),        W_d = W(d - 1),
+// piecewise linear in k with m + 1 jumps.  The reference's cdf_k = (W(k) / W_d)(1 + t), |t| <= e_k = 1.02 (k + 3) 2^-24
+// (the filter of b2w_walk_uw.cu), so with A = u W_d the reference's searchsorted(cdf, u) is the first k with
+// W(k) >= ceil(A (1 - e)), proven whenever that k also has W(k) >= ceil(A (1 + e + 2 e^2)).  The first k at or above
+// an integer threshold is found in closed form: a bisection over the m jump positions (W at a jump is monotone) and
+// one rounded-up division inside the linear segment.  No row is read at all: a step costs one 16-byte record, the
+// list words it bisects (m = 0 for most edges of a sparse graph) and one L2-resident indptr entry.  Steps the filter
+// cannot prove (~1 %: hub rows) replay the reference's f32 recurrence exactly from the same list (b2w_replay.cuh).
+// The step after the reference's unchecked choice == deg read (pecanpy.py:559; ~1e-7 of the steps) did not arrive
+// over a stored edge and is evaluated sequentially from the rows, as the oracle does (b2w_probs.cuh).
+//
+// One lane owns one walker (the PreComp mapping): 32 independent chains of dependent loads per warp and no
+// cross-lane traffic; the walk matrix is written per lane, L2 merges the sectors.
+//
+// Reference: pecanpy.py:164-210 (_random_walks), :522-561 (SparseOTF.get_move_forward),
+//            rw/sparse_rw.py:51-91 (get_normalized_probs), :142-230 (isnotin).
+#include <cmath>
+
+#include "b2w_probs.cuh"
+#include "b2w_replay.cuh"
+
+namespace {
+
+constexpr uint32_t NONE = 0xFFFFFFFFu;
+constexpr uint32_t KPF_POS_MASK = 0x3FFFFFFFu;
+constexpr uint32_t KPF_NOTFOUND = 0x40000000u;
+constexpr uint32_t KPF_HAS_TRI = 0x80000000u;
+constexpr int EW_THREADS = 256;
+
+struct EdgeConsts {
+  const uint4* __restrict__ rec;
+  const uint32_t* __restrict__ tri;
+  int a_in, a_out, a_ret;            // 1 / g, w_out / g, w_ret / g  (exact integers, (max_degree + 1) max(a) < 2^24)
+  double inv_in, inv_out;            // 1.0 / a_in, 1.0 / a_out
+  float g;                           // the common grid of the three weights (a power of two)
+};
+
+// The distribution of one step, in integer units of g.
+struct StepDist {
+  const uint32_t* __restrict__ lst;  // m sorted jump positions (common neighbours), none equal to kp
+  uint32_t m, kp, d;
+  int a_o, da, dr;
+  double inv;                        // 1.0 / a_o
+
+  // W at position k, given the number of list entries <= k
+  __device__ __forceinline__ int W(uint32_t k, uint32_t c_incl) const {
+    return (int)(k + 1) * a_o + (int)c_incl * da + (kp <= k ? dr : 0);
+  }
+  // smallest k in [lo, hi] with (k + 1) a_o + B >= T, or -1
+  __device__ __forceinline__ int seg(int lo, int hi, int B, int T) const {
+    const int need = T - B;
+    int k = lo;
+    if (need > a_o) {
+      int qv = (int)((double)need * inv);                             // ceil(need / a_o) within +-1
+      if (qv * a_o < need) ++qv;
+      if ((qv - 1) * a_o >= need) --qv;
+      k = max(qv - 1, lo);
+    }
+    return k <= hi ? k : -1;
+  }
+  // smallest k in [lo, hi] (c list entries lie before lo, none inside) with W(k) >= T, or -1
+  __device__ __forceinline__ int range(int lo, int hi, uint32_t c, int T) const {
+    const int B0 = (int)c * da;
+    if (hi < lo) return -1;
+    if (kp == NONE || kp > (uint32_t)hi) return seg(lo, hi, B0, T);
+    if (kp < (uint32_t)lo) return seg(lo, hi, B0 + dr, T);
+    if (kp > (uint32_t)lo) { const int r = seg(lo, (int)kp - 1, B0, T); if (r >= 0) return r; }
+    return seg((int)kp, hi, B0 + dr, T);
+  }
+  // first k with W(k) >= T (d - 1 when T exceeds the total); Wk receives W(k)
+  __device__ __forceinline__ uint32_t first_at_least(int T, int& Wk) const {
+    uint32_t lo = 0, hi = m;                                          // first jump i with W(p_i) >= T
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      const uint32_t pm = __ldg(lst + mid);
+      if (W(pm, mid + 1) >= T) hi = mid; else lo = mid + 1;
+    }
+    const uint32_t i = lo;
+    const int klo = i ? (int)__ldg(lst + i - 1) + 1 : 0;
+    const uint32_t pi = i < m ? __ldg(lst + i) : d;
+    const int r = range(klo, (int)pi - 1, i, T);
+    uint32_t k, c;
+    if (r >= 0) { k = (uint32_t)r; c = i; }
+    else if (i < m) { k = pi; c = i + 1; }
+    else { k = d - 1; c = m; }
+    Wk = W(k, c);
+    return k;
+  }
+};
+
+// Exact replay of the reference's f32 cumsum from the jump list (the list form of replay_exact in b2w_walk_uw.cu).
+__device__ __noinline__ uint32_t replay_list(const uint32_t* __restrict__ lst, const uint32_t m, const uint32_t d,
+                                             const uint32_t kp, const float fa, const float fo, const float fp,
+                                             const double u) {
+  float cdf = 0.f;
+  uint32_t k = 0, choice = d, ti = 0;
+  bool kp_left = kp != NONE;
+  uint32_t nextp = m ? __ldg(lst) : NONE;
+  for (;;) {
+    uint32_t pos;
+    bool is_kp;
+    if (kp_left && kp < nextp) { pos = kp; is_kp = true; }
+    else if (ti < m) { pos = nextp; is_kp = false; }
+    else break;
+    if (advance_run(cdf, k, pos - k, fo, u, choice)) return choice;
+    cdf = __fadd_rn(cdf, is_kp ? fp : fa);                            // the special element at `pos`
+    if (!((double)cdf < u)) return pos;
+    k = pos + 1;
+    if (is_kp) kp_left = false;
+    else { ++ti; nextp = ti < m ? __ldg(lst + ti) : NONE; }
+  }
+  if (advance_run(cdf, k, d - k, fo, u, choice)) return choice;
+  return d;                                                           // cdf[-1] < u: the reference's overflow
+}
+
+__device__ __forceinline__ uint32_t edge_step(const EdgeConsts& C, const uint32_t flags, const uint32_t d,
+                                              const bool has_prev, const uint32_t kpf, const uint32_t toff,
+                                              const double u, uint32_t& st_replays) {
+  StepDist D;
+  D.d = d;
+  D.m = 0; D.lst = C.tri; D.kp = NONE;
+  if (has_prev) {
+    if (!(kpf & KPF_NOTFOUND)) D.kp = kpf & KPF_POS_MASK;
+    if (kpf & KPF_HAS_TRI) { D.m = __ldg(C.tri + toff); D.lst = C.tri + toff + 1; }
+    D.a_o = C.a_out; D.inv = C.inv_out;
+  } else {
+    D.a_o = C.a_in; D.inv = C.inv_in;                                 // first step: every weight is 1
+  }
+  D.da = C.a_in - D.a_o;
+  D.dr = C.a_ret - D.a_o;
+  const int Wd = (int)d * D.a_o + (int)D.m * D.da + (D.kp != NONE ? D.dr : 0);
+  const double EC = 1.02 * 5.9604644775390625e-08;                    // 1.02 * 2^-24
+  const double A = u * (double)Wd;
+  bool replay = (flags & B2W_FLAG_FORCE_EXACT_REPLAY) != 0 || d > 160000u;
+  uint32_t choice = d;
+  if (!replay) {
+    // an upper bound of the answer from the most conservative "sure" threshold, then thresholds at that position
+    int Wk;
+    const double e_row = EC * (double)(d + 2);
+    const double t_hi = ceil(A * (1.0 + e_row + 2.0 * e_row * e_row + 2.9e-14));
+    uint32_t k_hi = d - 1;
+    if (t_hi <= (double)Wd) k_hi = D.first_at_least((int)t_hi, Wk);
+    const double e = EC * (double)(k_hi + 3);
+    const int T_poss = (int)ceil(A * (1.0 - e - 2.9e-14));
+    const double t_sure = ceil(A * (1.0 + e + 2.0 * e * e + 2.9e-14));
+    const uint32_t k = D.first_at_least(T_poss, Wk);                  // T_poss <= W_d: k exists, k <= k_hi
+    if ((double)Wk >= t_sure) choice = k; else replay = true;
+  }
+  if (replay) {
+    // the reference's probabilities: three exact f32 quotients by S = W_d g (rw/sparse_rw.py:89)
+    const float S = __fmul_rn(__int2float_rn(Wd), C.g);               // exact: W_d < 2^24, g a power of two
+    const float fa = __fdiv_rn(__fmul_rn(__int2float_rn(C.a_in), C.g), S);
+    const float fo = has_prev ? __fdiv_rn(__fmul_rn(__int2float_rn(C.a_out), C.g), S) : fa;
+    const float fp = __fdiv_rn(__fmul_rn(__int2float_rn(C.a_ret), C.g), S);
+    choice = replay_list(D.lst, D.m, d, D.kp, fa, fo, fp, u);
+    ++st_replays;
+  }
+  return choice;
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(EW_THREADS, MINB) walk_uw_edge_kernel(const WalkParams P, const EdgeConsts C) {
+  const uint32_t L = P.L;
+  uint32_t st_steps = 0, st_replays = 0, st_overflow = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)EW_THREADS + threadIdx.x; i < P.n_rows; i += (uint64_t)gridDim.x * EW_THREADS) {
+    uint32_t* const out = P.out + i * P.ld_out;
+    uint32_t cur = __ldg(P.start + i), prev = 0;
+    uint32_t cs = __ldg(P.indptr + cur);
+    uint32_t d = __ldg(P.indptr + cur + 1) - cs;
+    uint32_t kpf = 0, toff = 0, eff = L + 1;
+    bool edge_ok = true;                                              // the walker arrived over a stored edge
+    out[0] = cur;
+    uint32_t j = 1;
+    for (; j <= L; ++j) {
+      if (d == 0) { eff = j; break; }                                 // pecanpy.py:194-196, 204-206
+      const double u = step_uniform(P, i, j);
+      uint32_t choice;
+      if (edge_ok) choice = edge_step(C, P.flags, d, j > 1, kpf, toff, u, st_replays);
+      else choice = otf_choice_seq<false>(P, cur, true, prev, u);     // after an unchecked choice == deg read
+      if (choice == d) ++st_overflow;
+      edge_ok = choice < d;
+      const uint4 r = __ldg(C.rec + (cs + choice));                   // [cs + d] is the next row's first edge: pecanpy.py:559
+      prev = cur;
+      cur = r.x; kpf = r.y; toff = r.z; d = r.w;
+      out[j] = cur;
+      cs = __ldg(P.indptr + cur);
+      ++st_steps;
+    }
+    for (uint32_t z = j; z <= L; ++z) out[z] = 0u;                    // zero tail (np.zeros, pecanpy.py:182)
+    out[L + 1] = eff;
+  }
+  if (P.stats && !(P.flags & B2W_FLAG_NO_FILTER_STATS)) {
+    for (int o = 16; o; o >>= 1) {
+      st_steps += __shfl_xor_sync(B2W_FULL, st_steps, o);
+      st_replays += __shfl_xor_sync(B2W_FULL, st_replays, o);
+      st_overflow += __shfl_xor_sync(B2W_FULL, st_overflow, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (st_steps) atomicAdd((unsigned long long*)&P.stats->steps, (unsigned long long)st_steps);
+      if (st_replays) atomicAdd((unsigned long long*)&P.stats->exact_replays, (unsigned long long)st_replays);
+      if (st_overflow) atomicAdd((unsigned long long*)&P.stats->overflow_choices, (unsigned long long)st_overflow);
+    }
+  }
+}
+
+}  // namespace
+
+int b2w_launch_uw_edge(const b2w_graph* g, const WalkParams& P, cudaStream_t s) {
+  int gexp = 0;
+  if (!b2w_uw_grid(g, P.p, P.q, &gexp) || !(g->flags & B2W_GRAPH_HAS_EDGE_INDEX)) {
+    b2w_set_error("walk_uw_edge_kernel: graph / p / q not eligible or no edge index attached");
+    return B2W_ERR_INVALID;
+  }
+  EdgeConsts C;
+  C.rec = reinterpret_cast<const uint4*>(g->edge_rec);
+  C.tri = g->edge_tri;
+  C.g = ldexpf(1.0f, gexp);
+  C.a_in = (int)ldexp(1.0, -gexp);                                    // exact integers by construction of g
+  C.a_out = (int)ldexp((double)(float)(1.0 / P.q), -gexp);
+  C.a_ret = (int)ldexp((double)(float)(1.0 / P.p), -gexp);
+  C.inv_in = 1.0 / (double)C.a_in;
+  C.inv_out = 1.0 / (double)C.a_out;
+  const uint64_t want = (P.n_rows + EW_THREADS - 1) / EW_THREADS;
+  const uint64_t cap = (uint64_t)g->num_sms * 64;                     // grid-stride beyond a few waves
+  unsigned blocks = (unsigned)(want < cap ? want : cap);
+  if (blocks < 1) blocks = 1;
+  const int mb = (int)((P.flags >> 16) & 0xF);                        // tuning: resident CTAs per SM (0 = default)
+  if (mb == 8) walk_uw_edge_kernel<8><<<blocks, EW_THREADS, 0, s>>>(P, C);
+  else if (mb == 6) walk_uw_edge_kernel<6><<<blocks, EW_THREADS, 0, s>>>(P, C);
+  else if (mb == 4) walk_uw_edge_kernel<4><<<blocks, EW_THREADS, 0, s>>>(P, C);
+  else walk_uw_edge_kernel<5><<<blocks, EW_THREADS, 0, s>>>(P, C);
+  return b2w_cuda_fail(cudaGetLastError(), "walk_uw_edge_kernel launch");
+}

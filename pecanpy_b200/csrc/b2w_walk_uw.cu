@@ -32,6 +32,7 @@
 #include <cstring>
 
 #include "b2w_membership.cuh"
+#include "b2w_replay.cuh"
 
 namespace {
 
@@ -46,53 +47,6 @@ struct UwConsts {
   uint32_t gbm_stride;               // words of global bitmap scratch per group (0: never needed)
   uint32_t* gbm;                     // global bitmap scratch
 };
-
-__device__ __forceinline__ double pow2_double(int e) { return __hiloint2double((1023 + e) << 20, 0); }
-
-// Adds `fo` to the running f32 prefix `cdf` n times, exactly as n sequential __fadd_rn would, but
-// jumping through each binade of cdf in O(1): while cdf stays inside one binade its grid is
-// g = ulp(cdf), cdf is a multiple of g, and RN(cdf + fo) = cdf + RN_g(fo) whenever fo/g is not a
-// rounding tie (ties and binade crossings fall back to genuine single additions).  `k` is the
-// index of the next element; returns true and sets `choice` at the first element with !(cdf < u).
-__device__ __forceinline__ bool advance_run(float& cdf, uint32_t& k, uint32_t n, const float fo, const double u,
-                                            uint32_t& choice) {
-  while (n > 0) {
-    const uint32_t bits = __float_as_uint(cdf);
-    const int ex = (int)((bits >> 23) & 0xFFu);
-    if (ex >= 1 && ex < 255) {
-      const double t = (double)fo * pow2_double(150 - ex);            // fo / g, exact
-      if (t < 8388608.0) {
-        const double tr = rint(t);
-        if (fabs(t - tr) != 0.5) {
-          const uint32_t R = (uint32_t)tr;
-          if (R == 0) { k += n; return false; }                       // fo is absorbed: cdf never moves again
-          const uint32_t Cm = (bits & 0x7FFFFFu) | 0x800000u;         // cdf / g in [2^23, 2^24)
-          const uint32_t imax = (0xFFFFFFu - Cm) / R;                 // additions that stay below 2^24 g
-          const uint32_t steps = min(n, imax);
-          if (steps > 0) {
-            const uint32_t Cn = Cm + steps * R;
-            const float cdf_n = __uint_as_float((bits & 0xFF800000u) | (Cn & 0x7FFFFFu));
-            if (!((double)cdf_n < u)) {
-              const double U = u * pow2_double(150 - ex);             // u / g, exact scaling
-              double di = ceil((U - (double)Cm) / (double)R);
-              uint32_t i = di < 1.0 ? 1u : (di > (double)steps ? steps : (uint32_t)di);
-              while (i > 1 && (double)(Cm + (i - 1) * R) >= U) --i;
-              while ((double)(Cm + i * R) < U) ++i;
-              choice = k + i - 1;
-              return true;
-            }
-            cdf = cdf_n; k += steps; n -= steps;
-            if (n == 0) return false;
-          }
-        }
-      }
-    }
-    cdf = __fadd_rn(cdf, fo);                                          // genuine addition
-    if (!((double)cdf < u)) { choice = k; return true; }
-    ++k; --n;
-  }
-  return false;
-}
 
 template <int G>
 __device__ __noinline__ uint32_t replay_exact(const uint32_t* __restrict__ bm, const bool has_bm,
@@ -470,7 +424,7 @@ uint32_t gbm_stride(const b2w_graph* g) {
 
 // Exactness precondition of the analytic normaliser: 1, f32(1/q), f32(1/p) are multiples of one power of two g
 // and (max_degree + 1) * max(w) < 2^24 g.  Returns the exponent of g through `grid_exp` when eligible.
-static bool uw_grid(const b2w_graph* g, double p, double q, int* grid_exp) {
+bool b2w_uw_grid(const b2w_graph* g, double p, double q, int* grid_exp) {
   if (!(g->flags & B2W_GRAPH_UNWEIGHTED)) return false;
   const float w[3] = {1.0f, (float)(1.0 / q), (float)(1.0 / p)};
   int low = 1000;
@@ -494,7 +448,7 @@ static bool uw_grid(const b2w_graph* g, double p, double q, int* grid_exp) {
   return true;
 }
 
-bool b2w_uw_eligible(const b2w_graph* g, double p, double q) { return uw_grid(g, p, q, nullptr); }
+bool b2w_uw_eligible(const b2w_graph* g, double p, double q) { return b2w_uw_grid(g, p, q, nullptr); }
 
 size_t b2w_uw_work_bytes(const b2w_graph* g) {
   return 256 + (size_t)max_groups(g) * gbm_stride(g) * sizeof(uint32_t);
@@ -508,7 +462,7 @@ int b2w_launch_uw(const b2w_graph* g, const WalkParams& P_in, cudaStream_t s) {
   C.w_out = (float)(1.0 / P.q);
   C.w_ret = (float)(1.0 / P.p);
   int gexp = 0;
-  if (!uw_grid(g, P.p, P.q, &gexp)) { b2w_set_error("walk_uw_kernel: graph / p / q not eligible"); return B2W_ERR_INVALID; }
+  if (!b2w_uw_grid(g, P.p, P.q, &gexp)) { b2w_set_error("walk_uw_kernel: graph / p / q not eligible"); return B2W_ERR_INVALID; }
   C.g = ldexpf(1.0f, gexp);
   C.a_in = (uint32_t)ldexp(1.0, -gexp);                              // exact integers by construction of g
   C.a_out = (uint32_t)ldexp((double)C.w_out, -gexp);

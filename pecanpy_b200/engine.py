@@ -60,6 +60,10 @@ class WalkEngine:
         self._work: dict = {}
         self.alias: Optional[Tuple[np.ndarray, torch.Tensor, torch.Tensor]] = None
         self.last_stats = None
+        # per-edge index (b2w_edge_index.cu): "auto" = built on the first walk that can use it
+        self.edge_index_policy = os.environ.get("B2W_EDGE_INDEX", "auto")
+        self.edge_index_ms: Optional[float] = None
+        self._edge_index_failed = False
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -133,6 +137,69 @@ class WalkEngine:
                        "b2w_noise_thresholds")
         self.thr = thr
         return thr
+
+    # ------------------------------------------------------------------ per-edge index
+    @property
+    def has_edge_index(self) -> bool:
+        return bool(self.info().flags & capi.GRAPH_HAS_EDGE_INDEX)
+
+    def build_edge_index(self) -> bool:
+        """Build the per-edge index on the GPU (b2w_edge_index_prepare / _finish) and attach it to the handle.
+        Returns False (and leaves the on-the-fly kernels in charge) when the lists do not fit 32-bit offsets or
+        the device memory does not hold them."""
+        if self.kind != "csr":
+            raise ValueError("the edge index needs a CSR graph")
+        if self.has_edge_index:
+            return True
+        gi = self.info()
+        with torch.cuda.device(self.device):
+            free, _ = torch.cuda.mem_get_info(self.device)
+            rec_bytes = 16 * (gi.nnz + 1)
+            wb = int(self.lib.b2w_edge_index_work_bytes(self.handle))
+            if rec_bytes + wb > 0.6 * free:
+                self._edge_index_failed = True
+                return False
+            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            t0.record()
+            rec = torch.empty(4 * (gi.nnz + 1), dtype=torch.int32, device=self.device)
+            work = torch.empty(wb, dtype=torch.uint8, device=self.device)
+            words = C.c_uint64(0)
+            rc = self.lib.b2w_edge_index_prepare(self.handle, _ptr(rec), _ptr(work), wb, C.byref(words),
+                                                 C.c_void_p(stream))
+            if rc == capi.ERR_UNSUPPORTED or (rc == capi.OK and 4 * words.value > 0.6 * free):
+                self._edge_index_failed = True
+                return False
+            capi.check(rc, "b2w_edge_index_prepare")
+            tri = torch.empty(max(int(words.value), 1), dtype=torch.int32, device=self.device)
+            capi.check(self.lib.b2w_edge_index_finish(self.handle, _ptr(rec), _ptr(tri), int(words.value), _ptr(work),
+                                                      wb, C.c_void_p(stream)), "b2w_edge_index_finish")
+            t1.record()
+            t1.synchronize()
+            self.edge_index_ms = t0.elapsed_time(t1)
+        self._keep["edge_rec"], self._keep["edge_tri"] = rec, tri
+        self.edge_index_words = int(words.value)
+        return True
+
+    def drop_edge_index(self):
+        if self.kind == "csr" and self.handle:
+            capi.check(self.lib.b2w_graph_set_edge_index(self.handle, None, None, 0), "b2w_graph_set_edge_index")
+        self._keep.pop("edge_rec", None)
+        self._keep.pop("edge_tri", None)
+
+    def _maybe_edge_index(self, mode: int, p: float, q: float, extend: bool, flags: int):
+        """Policy "auto": build the index before the first walk whose kernel can use it (unweighted SparseOTF with
+        exactly representable biases; PreComp)."""
+        if self.kind != "csr" or self.edge_index_policy in ("0", "off", "never") or self._edge_index_failed:
+            return
+        if flags & capi.FLAG_NO_EDGE_INDEX or self.has_edge_index:
+            return
+        want = mode == capi.MODE_PRECOMP
+        if mode == capi.MODE_SPARSE_OTF and not extend:
+            name = self.lib.b2w_walk_kernel_name(self.handle, mode, float(p), float(q), 0, int(flags)).decode()
+            want = name == "walk_uw_kernel"
+        if want:
+            self.build_edge_index()
 
     def _scratch(self, key: str, nbytes: int) -> Optional[torch.Tensor]:
         if nbytes == 0:
@@ -210,6 +277,7 @@ class WalkEngine:
                 d_feed = feed if isinstance(feed, torch.Tensor) else _to_dev(np.ascontiguousarray(feed, np.float64), self.device)
                 if d_feed.numel() != n_rows * walk_length:
                     raise ValueError("feed must hold n_rows * walk_length doubles")
+            self._maybe_edge_index(mode, p, q, bool(extend), int(flags))
             wb = int(self.lib.b2w_walk_work_bytes(self.handle, mode))
             work = self._scratch("walk", wb)
             stats_t = torch.zeros(4, dtype=torch.int64, device=self.device) if collect_stats else None
@@ -248,6 +316,7 @@ class WalkEngine:
         st = capi.WalkStats()
         thr = self.thr if extend else None
         with torch.cuda.device(self.device):
+            self._maybe_edge_index(mode, p, q, bool(extend), int(flags))
             capi.check(self.lib.b2w_walk_host(self.handle, mode, float(p), float(q), int(bool(extend)), _ptr(thr),
                                               C.c_void_p(start.ctypes.data), int(row0), n_rows, int(walk_length),
                                               int(seed) & (2 ** 64 - 1), C.c_void_p(out.ctypes.data), int(batch_rows),

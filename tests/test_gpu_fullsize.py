@@ -1,6 +1,6 @@
 """Parity at BASELINE.json's full sizes through size-independent properties (the oracle cannot walk
 10^7 rows in test time): every step is an edge of the graph, rows are well formed, independent kernel
-variants (membership-bitmap kernel, generic weight-streaming kernel) produce IDENTICAL matrices, a
+variants (edge-index kernel, membership-bitmap kernel, generic weight-streaming kernel) produce IDENTICAL matrices, a
 prefix of the rows equals the oracle, and the result does not depend on how rows are sharded."""
 import numpy as np
 import pytest
@@ -61,11 +61,16 @@ def test_full_size_sparse_otf(workload):
     n, L = indptr.size - 1, 80
     start = synth.shuffled_start(n, num_walks, 0)
     eng = WalkEngine.from_csr(indptr, indices, data, device=dev)
-    a = eng.walk("SparseOTF", p, q, start, L, seed=5)                      # membership-bitmap kernel
-    assert eng.kernel_name("SparseOTF", p, q) == "walk_uw_kernel"
+    a = eng.walk("SparseOTF", p, q, start, L, seed=5)                      # edge-index kernel (index built on demand)
+    assert eng.kernel_name("SparseOTF", p, q) == "walk_uw_edge_kernel"
     st = eng.stats()
+    m = eng.walk("SparseOTF", p, q, start, L, seed=5, flags=0x40)          # membership-bitmap kernel
+    assert eng.kernel_name("SparseOTF", p, q, flags=0x40) == "walk_uw_kernel"
+    assert torch.equal(a, m), "edge-index and membership kernels disagree at full size"
+    del m
     b = eng.walk("SparseOTF", p, q, start, L, seed=5, flags=8)             # generic weight-streaming kernel
     assert torch.equal(a, b), "kernel variants disagree at full size"
+    del b
     assert st["steps"] == eng.count_steps(a, L)
     # the only steps that may leave the edge set are the reference's own unchecked `choice == deg` reads
     # (cdf[-1] < u, ~1e-7 per step), which the engine reproduces and counts

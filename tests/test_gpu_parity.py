@@ -64,11 +64,13 @@ def test_philox_device_known_answers(mods):
 
 
 # b2w_walk flags: 1 forced replay, 4 lane-per-walker kernel, 8 generic (weight-streaming) kernel even on
-# unweighted graphs, 0x20 membership by binary search only (no shared-memory hash set), bits 8..15 lanes per
-# walker of the unweighted membership-bitmap kernel
+# unweighted graphs, 0x20 warp-cooperative state-machine kernel (sub-warp groups), 0x40 ignore the per-edge index
+# (on-the-fly membership kernels), bits 8..15 lanes per walker of the membership-bitmap kernel (which also routes
+# around the edge-index kernel).  "auto" on an unweighted graph with representable biases = the edge-index kernel.
 FLAG_SETS = {"auto": 0, "auto-replay": 1, "lane-per-walker": 4, "generic": 8, "generic-replay": 9,
+             "membership": 0x40, "membership-replay": 0x41,
              "uw-g8": 8 << 8, "uw-g16": 16 << 8, "uw-g32": 32 << 8, "uw-g8-replay": (8 << 8) | 1,
-             "uw-g32-replay": (32 << 8) | 1, "uw-nohash": 0x20, "generic-nohash": 0x28, "uw-g16-nohash": (16 << 8) | 0x20}
+             "uw-g32-replay": (32 << 8) | 1, "uw-coop": 0x20, "generic-coop": 0x28, "uw-g16-coop": (16 << 8) | 0x20}
 
 SPARSE_R1 = ["testwalk_SparseOTF", "karate_sparseotf_p1_q1", "karate_sparseotf_p05_q2", "karate_sparseotf_p03_q07",
              "w200_sparseotf_n2v", "w200_sparseotf_ext_g0", "w200_sparseotf_ext_g05", "hub400_sparseotf_n2v",
