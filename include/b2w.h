@@ -171,6 +171,15 @@ int b2w_alias_build(const b2w_graph* g, double p, double q, int extend, const fl
                     const uint64_t* d_alias_indptr, uint32_t* d_alias_j, float* d_alias_q,
                     void* d_work, size_t work_bytes, void* stream);
 
+/* The same tables in ONE array of 8-byte entries { float q; uint32 j } (little endian: q in the low word), so that an
+ * alias draw (pecanpy.py:668-677: q[kk], then maybe j[kk]) touches one memory sector instead of two.  Entry e is the
+ * pair (alias_q[e], alias_j[e]) of the reference's arrays, bit for bit; d_alias_qj needs alias_indptr[n] + max_degree
+ * entries, 8-byte aligned.  Attach with b2w_graph_set_alias_packed. */
+int b2w_alias_build_packed(const b2w_graph* g, double p, double q, int extend, const float* d_thr,
+                           const uint64_t* d_alias_indptr, uint64_t* d_alias_qj, void* d_work, size_t work_bytes,
+                           void* stream);
+int b2w_graph_set_alias_packed(b2w_graph* g, const uint64_t* d_alias_indptr, const uint64_t* d_alias_qj);
+
 /* PreCompFirstOrder tables (pecanpy.py:336-361): one table per node, laid out like `data`. */
 int b2w_alias_build_first_order(const b2w_graph* g, uint32_t* d_alias_j, float* d_alias_q,
                                 void* d_work, size_t work_bytes, void* stream);

@@ -14,27 +14,30 @@
 
 namespace {
 
+// ST = element stride of q[] and j[]: 1 for the reference's two arrays, 2 for the packed {q, j} table
+template <int ST>
 __device__ __forceinline__ void alias_setup_inplace(uint32_t k, uint32_t* __restrict__ j, float* __restrict__ q,
                                                     uint32_t* __restrict__ stk) {
   // on entry q[kk] holds the normalised probability probs[kk]
   uint32_t sp = 0, lp = 0;   // smaller grows up from stk[0], larger grows down from stk[k-1]
   for (uint32_t kk = 0; kk < k; ++kk) {
-    float v = (float)__dmul_rn((double)k, (double)q[kk]);             // q[kk] = k * probs[kk] (:642)
-    q[kk] = v;
-    j[kk] = 0;
+    float v = (float)__dmul_rn((double)k, (double)q[kk * ST]);        // q[kk] = k * probs[kk] (:642)
+    q[kk * ST] = v;
+    j[kk * ST] = 0;
     if (v < 1.0f) stk[sp++] = kk; else stk[k - 1 - lp++] = kk;
   }
   while (sp > 0 && lp > 0) {                                          // (:650-663)
     uint32_t small = stk[--sp];
     uint32_t large = stk[k - 1 - (--lp)];
-    j[small] = large;
-    float v = (float)__dsub_rn((double)__fadd_rn(q[large], q[small]), 1.0);
-    q[large] = v;
+    j[small * ST] = large;
+    float v = (float)__dsub_rn((double)__fadd_rn(q[large * ST], q[small * ST]), 1.0);
+    q[large * ST] = v;
     if (v < 1.0f) stk[sp++] = large; else stk[k - 1 - lp++] = large;
   }
 }
 
-template <bool EXTEND, bool FIRST_ORDER>
+// PACKED: alias_q points at the packed table (uint2 {q bits, j} per entry, b2w_alias_build_packed), alias_j is unused
+template <bool EXTEND, bool FIRST_ORDER, bool PACKED>
 __global__ void __launch_bounds__(128) alias_build_kernel(const WalkParams P, const uint64_t* __restrict__ aip,
                                                           uint32_t* __restrict__ alias_j,
                                                           float* __restrict__ alias_q, uint32_t* __restrict__ work,
@@ -64,17 +67,18 @@ __global__ void __launch_bounds__(128) alias_build_kernel(const WalkParams P, co
       prev = P.indices[t];
       off = aip[idx] + (uint64_t)deg * nb;                            // (:501)
     }
-    float* q = alias_q + off;
-    uint32_t* j = alias_j + off;
+    constexpr int ST = PACKED ? 2 : 1;
+    float* q = alias_q + off * ST;
+    uint32_t* j = PACKED ? reinterpret_cast<uint32_t*>(q) + 1 : alias_j + off;
     BiasStream<EXTEND> bs(P, idx, !FIRST_ORDER, prev);
     float sum = 0.f;
     for (uint32_t k = 0; k < deg; ++k) {
       float w = bs.weight(k);
-      q[k] = w;
+      q[k * ST] = w;
       sum = __fadd_rn(sum, w);                                        // sequential f32 sum
     }
-    for (uint32_t k = 0; k < deg; ++k) q[k] = __fdiv_rn(q[k], sum);   // rw/sparse_rw.py:89
-    alias_setup_inplace(deg, j, q, stk);
+    for (uint32_t k = 0; k < deg; ++k) q[k * ST] = __fdiv_rn(q[k * ST], sum);   // rw/sparse_rw.py:89
+    alias_setup_inplace<ST>(deg, j, q, stk);
   }
 }
 
@@ -87,7 +91,7 @@ constexpr int ALIAS_SMEM_DEG = 64;
 constexpr int ALIAS_WARPS = 4;
 constexpr int ALIAS_PITCH = 33;
 
-template <bool EXTEND, bool FIRST_ORDER>
+template <bool EXTEND, bool FIRST_ORDER, bool PACKED>
 __global__ void __launch_bounds__(ALIAS_WARPS * 32) alias_build_smem_kernel(const WalkParams P,
                                                                              const uint64_t* __restrict__ aip,
                                                                              uint32_t* __restrict__ alias_j,
@@ -155,8 +159,12 @@ __global__ void __launch_bounds__(ALIAS_WARPS * 32) alias_build_smem_kernel(cons
       const uint32_t dg = __shfl_sync(B2W_FULL, deg, s2);
       const uint64_t of = __shfl_sync(B2W_FULL, off, s2);
       for (uint32_t k = lane; k < dg; k += 32) {
-        alias_q[of + k] = sq[k * ALIAS_PITCH + s2];
-        alias_j[of + k] = sj[k * ALIAS_PITCH + s2];
+        if (PACKED) {
+          reinterpret_cast<uint2*>(alias_q)[of + k] = make_uint2(__float_as_uint(sq[k * ALIAS_PITCH + s2]), sj[k * ALIAS_PITCH + s2]);
+        } else {
+          alias_q[of + k] = sq[k * ALIAS_PITCH + s2];
+          alias_j[of + k] = sj[k * ALIAS_PITCH + s2];
+        }
       }
     }
     __syncwarp();
@@ -187,9 +195,9 @@ static bool g_alias_force_global = false;   // test hook (B2W_ALIAS_FORCE_GLOBAL
 
 static int alias_build_common(const b2w_graph* g, double p, double q, int extend, const float* d_thr,
                               const uint64_t* aip, uint32_t* aj, float* aq, void* d_work, size_t work_bytes,
-                              void* stream, bool first_order) {
+                              void* stream, bool first_order, bool packed = false) {
   if (!g || !(g->flags & B2W_GRAPH_CSR)) { b2w_set_error("alias build: CSR graph handle required"); return B2W_ERR_INVALID; }
-  if (!aj || !aq || (!first_order && !aip)) { b2w_set_error("alias build: null output/offset pointer"); return B2W_ERR_INVALID; }
+  if ((!packed && !aj) || !aq || (!first_order && !aip)) { b2w_set_error("alias build: null output/offset pointer"); return B2W_ERR_INVALID; }
   if (extend && !d_thr) { b2w_set_error("alias build: extend requires noise thresholds"); return B2W_ERR_INVALID; }
   if (!(p > 0.0) || !(q > 0.0)) { b2w_set_error("alias build: p and q must be > 0"); return B2W_ERR_INVALID; }
   size_t need = b2w_alias_build_work_bytes(g);
@@ -209,14 +217,14 @@ static int alias_build_common(const b2w_graph* g, double p, double q, int extend
     uint64_t nb = (n_tables + 32 * ALIAS_WARPS - 1) / (32 * ALIAS_WARPS);
     uint64_t cap = (uint64_t)g->num_sms * 16;
     unsigned blocks = (unsigned)(nb < cap ? nb : cap);
-#define B2W_ALIAS_SMEM(E, F)                                                                                        \
+#define B2W_ALIAS_SMEM(E, F, K)                                                                                     \
     do {                                                                                                            \
-      B2W_CUDA(cudaFuncSetAttribute(alias_build_smem_kernel<E, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      alias_build_smem_kernel<E, F><<<blocks, ALIAS_WARPS * 32, smem, s>>>(P, aip, aj, aq, n_tables);             \
+      B2W_CUDA(cudaFuncSetAttribute(alias_build_smem_kernel<E, F, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      alias_build_smem_kernel<E, F, K><<<blocks, ALIAS_WARPS * 32, smem, s>>>(P, aip, aj, aq, n_tables);          \
     } while (0)
-    if (first_order) B2W_ALIAS_SMEM(false, true);
-    else if (extend) B2W_ALIAS_SMEM(true, false);
-    else B2W_ALIAS_SMEM(false, false);
+    if (first_order) B2W_ALIAS_SMEM(false, true, false);
+    else if (extend) { if (packed) B2W_ALIAS_SMEM(true, false, true); else B2W_ALIAS_SMEM(true, false, false); }
+    else { if (packed) B2W_ALIAS_SMEM(false, false, true); else B2W_ALIAS_SMEM(false, false, false); }
 #undef B2W_ALIAS_SMEM
     return b2w_cuda_fail(cudaGetLastError(), "alias_build_smem_kernel launch");
   }
@@ -224,11 +232,15 @@ static int alias_build_common(const b2w_graph* g, double p, double q, int extend
   if (blocks > lanes / 128) blocks = lanes / 128;
   uint32_t stride = g->max_degree ? g->max_degree : 1;
   if (first_order)
-    alias_build_kernel<false, true><<<(unsigned)blocks, 128, 0, s>>>(P, aip, aj, aq, (uint32_t*)d_work, stride, n_tables);
+    alias_build_kernel<false, true, false><<<(unsigned)blocks, 128, 0, s>>>(P, aip, aj, aq, (uint32_t*)d_work, stride, n_tables);
+  else if (extend && packed)
+    alias_build_kernel<true, false, true><<<(unsigned)blocks, 128, 0, s>>>(P, aip, aj, aq, (uint32_t*)d_work, stride, n_tables);
   else if (extend)
-    alias_build_kernel<true, false><<<(unsigned)blocks, 128, 0, s>>>(P, aip, aj, aq, (uint32_t*)d_work, stride, n_tables);
+    alias_build_kernel<true, false, false><<<(unsigned)blocks, 128, 0, s>>>(P, aip, aj, aq, (uint32_t*)d_work, stride, n_tables);
+  else if (packed)
+    alias_build_kernel<false, false, true><<<(unsigned)blocks, 128, 0, s>>>(P, aip, aj, aq, (uint32_t*)d_work, stride, n_tables);
   else
-    alias_build_kernel<false, false><<<(unsigned)blocks, 128, 0, s>>>(P, aip, aj, aq, (uint32_t*)d_work, stride, n_tables);
+    alias_build_kernel<false, false, false><<<(unsigned)blocks, 128, 0, s>>>(P, aip, aj, aq, (uint32_t*)d_work, stride, n_tables);
   return b2w_cuda_fail(cudaGetLastError(), "alias_build_kernel launch");
 }
 
@@ -246,6 +258,14 @@ extern "C" int b2w_alias_build(const b2w_graph* g, double p, double q, int exten
                                void* d_work, size_t work_bytes, void* stream) {
   return alias_build_common(g, p, q, extend, d_thr, d_alias_indptr, d_alias_j, d_alias_q, d_work, work_bytes,
                             stream, false);
+}
+
+extern "C" int b2w_alias_build_packed(const b2w_graph* g, double p, double q, int extend, const float* d_thr,
+                                      const uint64_t* d_alias_indptr, uint64_t* d_alias_qj, void* d_work,
+                                      size_t work_bytes, void* stream) {
+  if (d_alias_qj && (reinterpret_cast<uintptr_t>(d_alias_qj) & 7) != 0) { b2w_set_error("alias build: packed table must be 8-byte aligned"); return B2W_ERR_INVALID; }
+  return alias_build_common(g, p, q, extend, d_thr, d_alias_indptr, nullptr, reinterpret_cast<float*>(d_alias_qj), d_work,
+                            work_bytes, stream, false, true);
 }
 
 extern "C" int b2w_alias_build_first_order(const b2w_graph* g, uint32_t* d_alias_j, float* d_alias_q,

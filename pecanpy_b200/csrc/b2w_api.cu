@@ -2,6 +2,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -140,6 +141,15 @@ static int new_handle(int device, b2w_graph** out, b2w_graph** gp) {
   cudaError_t e = cudaGetDeviceProperties(&prop, device);
   if (e != cudaSuccess) { delete g; return b2w_cuda_fail(e, "cudaGetDeviceProperties"); }
   g->num_sms = prop.multiProcessorCount;
+  {
+    // The walk kernels gather 16-byte records / 4-byte entries at random: ask L2 to fetch single 32-byte sectors
+    // from DRAM instead of the default 64 bytes (ncu, round 2: 2.4 DRAM sectors per gathered sector).  A hint,
+    // per device; B2W_L2_FETCH=0 leaves the device setting alone, any other value is passed on.
+    const char* e = getenv("B2W_L2_FETCH");
+    const long v = e ? strtol(e, nullptr, 10) : 32;
+    if (v > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v);
+    cudaGetLastError();
+  }
   g->pipe = new (std::nothrow) b2w_host_pipe();
   if (!g->pipe) { delete g; b2w_set_error("graph create: out of host memory"); return B2W_ERR_NOMEM; }
   *gp = g;
@@ -225,8 +235,16 @@ extern "C" void b2w_graph_destroy(b2w_graph* g) {
 
 extern "C" int b2w_graph_set_alias(b2w_graph* g, const uint64_t* aip, const uint32_t* aj, const float* aq) {
   if (!g || !(g->flags & B2W_GRAPH_CSR)) { b2w_set_error("set_alias: CSR graph handle required"); return B2W_ERR_INVALID; }
-  g->alias_indptr = aip; g->alias_j = aj; g->alias_q = aq;
+  g->alias_indptr = aip; g->alias_j = aj; g->alias_q = aq; g->alias_qj = nullptr;
   if (aj && aq) g->flags |= B2W_GRAPH_HAS_ALIAS; else g->flags &= ~B2W_GRAPH_HAS_ALIAS;
+  return B2W_OK;
+}
+
+extern "C" int b2w_graph_set_alias_packed(b2w_graph* g, const uint64_t* aip, const uint64_t* aqj) {
+  if (!g || !(g->flags & B2W_GRAPH_CSR)) { b2w_set_error("set_alias_packed: CSR graph handle required"); return B2W_ERR_INVALID; }
+  if (aqj && !aip) { b2w_set_error("set_alias_packed: the packed layout is for PreComp tables (needs alias_indptr)"); return B2W_ERR_INVALID; }
+  g->alias_indptr = aip; g->alias_j = nullptr; g->alias_q = nullptr; g->alias_qj = reinterpret_cast<const uint2*>(aqj);
+  if (aqj) g->flags |= B2W_GRAPH_HAS_ALIAS; else g->flags &= ~B2W_GRAPH_HAS_ALIAS;
   return B2W_OK;
 }
 
@@ -297,7 +315,7 @@ extern "C" int b2w_walk(const b2w_graph* g, int mode, double p, double q, int ex
   WalkParams P{};
   P.n = g->n; P.indptr = g->indptr; P.indices = g->indices; P.data = g->data;
   P.dense = g->dense; P.nonzero = g->nonzero; P.thr = d_thr;
-  P.alias_indptr = g->alias_indptr; P.alias_j = g->alias_j; P.alias_q = g->alias_q;
+  P.alias_indptr = g->alias_indptr; P.alias_j = g->alias_j; P.alias_q = g->alias_q; P.alias_qj = g->alias_qj;
   P.start = d_start; P.feed = d_feed; P.out = d_out; P.ld_out = ld_out;
   P.row0 = row0; P.n_rows = n_rows; P.L = walk_length;
   P.key0 = (uint32_t)seed; P.key1 = (uint32_t)(seed >> 32);
@@ -316,6 +334,13 @@ extern "C" int b2w_walk(const b2w_graph* g, int mode, double p, double q, int ex
     }
     return b2w_launch_sparse_warp(g, P, s);
   }
+  if (mode == B2W_MODE_PRECOMP_FIRST_ORDER && g->alias_qj) {
+    b2w_set_error("b2w_walk: PreCompFirstOrder needs the two-array tables (b2w_graph_set_alias)");
+    return B2W_ERR_INVALID;
+  }
+  // PreComp through the per-edge index: no search of prev in row(cur), one record per step (b2w_walk_edge.cu)
+  if (mode == B2W_MODE_PRECOMP && (g->flags & B2W_GRAPH_HAS_EDGE_INDEX) && !(flags & B2W_FLAG_NO_EDGE_INDEX))
+    return b2w_launch_precomp_edge(g, P, s);
   return b2w_launch_thread_walk(g, mode, ext, P, s);
 }
 
@@ -323,7 +348,9 @@ extern "C" const char* b2w_walk_kernel_name(const b2w_graph* g, int mode, double
   if (!g) return "";
   switch (mode) {
     case B2W_MODE_DENSE_OTF: return "walk_dense_kernel";
-    case B2W_MODE_PRECOMP: return "walk_thread_kernel<PRECOMP>";
+    case B2W_MODE_PRECOMP:
+      if ((g->flags & B2W_GRAPH_HAS_EDGE_INDEX) && !(flags & B2W_FLAG_NO_EDGE_INDEX)) return "walk_precomp_edge_kernel";
+      return "walk_thread_kernel<PRECOMP>";
     case B2W_MODE_FIRST_ORDER_UNWEIGHTED: return "walk_thread_kernel<FIRST_ORDER_UNWEIGHTED>";
     case B2W_MODE_PRECOMP_FIRST_ORDER: return "walk_thread_kernel<PRECOMP_FIRST_ORDER>";
     case B2W_MODE_SPARSE_OTF:

@@ -27,6 +27,7 @@ struct b2w_graph {
   const uint64_t* alias_indptr;
   const uint32_t* alias_j;
   const float* alias_q;
+  const uint2* alias_qj;   // packed {q bits, j} table (b2w_alias_build_packed); alias_j / alias_q are then null
   // per-edge index (borrowed; b2w_edge_index.cu)
   const void* edge_rec;
   const uint32_t* edge_tri;
@@ -47,6 +48,7 @@ struct WalkParams {
   const uint64_t* __restrict__ alias_indptr;
   const uint32_t* __restrict__ alias_j;
   const float* __restrict__ alias_q;
+  const uint2* __restrict__ alias_qj;
   const uint32_t* __restrict__ start;
   const double* __restrict__ feed;
   uint32_t* __restrict__ out;
@@ -161,5 +163,6 @@ bool b2w_uw_eligible(const b2w_graph* g, double p, double q);
 size_t b2w_uw_work_bytes(const b2w_graph* g);
 int b2w_launch_uw(const b2w_graph* g, const WalkParams& P, cudaStream_t s);
 int b2w_launch_uw_edge(const b2w_graph* g, const WalkParams& P, cudaStream_t s);
+int b2w_launch_precomp_edge(const b2w_graph* g, const WalkParams& P, cudaStream_t s);
 bool b2w_uw_grid(const b2w_graph* g, double p, double q, int* grid_exp);
 uint32_t b2w_sparse_warp_total_warps(const b2w_graph* g);

@@ -90,14 +90,26 @@ extern "C" int b2w_edgelist_parse(const char* path, int weighted, const char* de
   FILE* f = fopen(path, "rb");
   if (!f) { b2w_set_error("b2w_edgelist_parse: cannot open %s: %s", path, strerror(errno)); return B2W_ERR_INVALID; }
   std::string buf;
-  {
+  try {
     char chunk[1 << 16];
     size_t got;
     while ((got = fread(chunk, 1, sizeof chunk, f)) > 0) buf.append(chunk, got);
+  } catch (const std::bad_alloc&) {
     fclose(f);
+    b2w_set_error("b2w_edgelist_parse: out of memory");
+    return B2W_ERR_NOMEM;
   }
-  for (unsigned char c : buf)
-    if (c >= 0x80) { b2w_set_error("b2w_edgelist_parse: non-ASCII input (use the Unicode-aware Python parser)"); return B2W_ERR_UNSUPPORTED; }
+  fclose(f);
+  // Inputs on which this byte-level parser and the reference's text-mode read could disagree are left to the Python
+  // parser (B2W_ERR_UNSUPPORTED): non-ASCII bytes (str.strip() is Unicode aware), NUL (the id blob is NUL separated),
+  // a bare '\r' (universal newlines make it a line end).
+  for (size_t i = 0; i < buf.size(); ++i) {
+    const unsigned char c = (unsigned char)buf[i];
+    if (c >= 0x80 || c == 0 || (c == '\r' && (i + 1 == buf.size() || buf[i + 1] != '\n'))) {
+      b2w_set_error("b2w_edgelist_parse: non-ASCII / NUL / bare CR in the input (use the Python parser)");
+      return B2W_ERR_UNSUPPORTED;
+    }
+  }
   b2w_edgelist* E = new (std::nothrow) b2w_edgelist();
   if (!E) { b2w_set_error("b2w_edgelist_parse: out of memory"); return B2W_ERR_NOMEM; }
   E->ids.init(1u << 16);
@@ -149,6 +161,11 @@ extern "C" int b2w_edgelist_parse(const char* path, int weighted, const char* de
         while (tle > tl && is_py_space((unsigned char)tle[-1])) --tle;
         std::string tok(tl, tle);
         char* stop = nullptr;
+        if (tok.find_first_of("_(") != std::string::npos) {             // float() accepts 1_0 and rejects nan(1): strtod differs
+          delete E;
+          b2w_set_error("b2w_edgelist_parse: weight token '%s' needs Python's float() (line %llu)", tok.c_str(), (unsigned long long)line_no);
+          return B2W_ERR_UNSUPPORTED;
+        }
         bool bad = tok.empty() || tok.find_first_of("xXpP") != std::string::npos;   // float() has no hex floats
         if (!bad) { weight = strtod(tok.c_str(), &stop); bad = stop != tok.c_str() + tok.size(); }
         if (bad) {

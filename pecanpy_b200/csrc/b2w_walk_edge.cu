@@ -18,7 +18,7 @@
 // over a stored edge and is evaluated sequentially from the rows, as the oracle does (b2w_probs.cuh).
 //
 // One lane owns one walker (the PreComp mapping): 32 independent chains of dependent loads per warp and no
-// cross-lane traffic; the walk matrix is written per lane, L2 merges the sectors.
+// cross-lane traffic; every lane stages its row in shared memory and writes complete 32-byte sectors (b2w_rowout.cuh).
 //
 // Reference: pecanpy.py:164-210 (_random_walks), :522-561 (SparseOTF.get_move_forward),
 //            rw/sparse_rw.py:51-91 (get_normalized_probs), :142-230 (isnotin).
@@ -26,6 +26,7 @@
 
 #include "b2w_probs.cuh"
 #include "b2w_replay.cuh"
+#include "b2w_rowout.cuh"
 
 namespace {
 
@@ -54,29 +55,25 @@ struct StepDist {
   __device__ __forceinline__ int W(uint32_t k, uint32_t c_incl) const {
     return (int)(k + 1) * a_o + (int)c_incl * da + (kp <= k ? dr : 0);
   }
-  // smallest k in [lo, hi] with (k + 1) a_o + B >= T, or -1
-  __device__ __forceinline__ int seg(int lo, int hi, int B, int T) const {
-    const int need = T - B;
-    int k = lo;
-    if (need > a_o) {
-      int qv = (int)((double)need * inv);                             // ceil(need / a_o) within +-1
-      if (qv * a_o < need) ++qv;
-      if ((qv - 1) * a_o >= need) --qv;
-      k = max(qv - 1, lo);
-    }
-    return k <= hi ? k : -1;
+  // ceil(need / a_o)  (any sign; |need| < 2^26)
+  __device__ __forceinline__ int ceil_div(const int need) const {
+    int qv = __double2int_rz((double)need * inv);                     // within +-1 of the quotient
+    if (qv * a_o < need) ++qv;
+    if ((qv - 1) * a_o >= need) --qv;
+    return qv;
   }
-  // smallest k in [lo, hi] (c list entries lie before lo, none inside) with W(k) >= T, or -1
-  __device__ __forceinline__ int range(int lo, int hi, uint32_t c, int T) const {
-    const int B0 = (int)c * da;
-    if (hi < lo) return -1;
-    if (kp == NONE || kp > (uint32_t)hi) return seg(lo, hi, B0, T);
-    if (kp < (uint32_t)lo) return seg(lo, hi, B0 + dr, T);
-    if (kp > (uint32_t)lo) { const int r = seg(lo, (int)kp - 1, B0, T); if (r >= 0) return r; }
-    return seg((int)kp, hi, B0 + dr, T);
+  // smallest k in [lo, hi] with W(k) >= T, or -1, when no list entry lies inside [lo, hi] and B0 = c da for the c
+  // entries before lo.  The jump of kp splits the range in at most two linear pieces; both candidates are formed
+  // without branching (lanes of a warp disagree on where kp falls).
+  __device__ __forceinline__ int range(const int lo, const int hi, const int B0, const int T) const {
+    const bool kp_in = hi >= 0 && kp <= (uint32_t)hi;                 // (NONE never is)
+    const int hiA = kp_in ? (int)kp - 1 : hi;                         // an empty range (hi < lo) fails both tests below
+    const int kA = max(ceil_div(T - B0) - 1, lo);                     // piece before kp: (k + 1) a_o + B0 >= T
+    const int kB = max(ceil_div(T - B0 - dr) - 1, max(lo, (int)kp));  // piece from kp on
+    return kA <= hiA ? kA : ((kp_in && kB <= hi) ? kB : -1);
   }
   // first k with W(k) >= T (d - 1 when T exceeds the total); Wk receives W(k)
-  __device__ __forceinline__ uint32_t first_at_least(int T, int& Wk) const {
+  __device__ __forceinline__ uint32_t first_at_least(const int T, int& Wk) const {
     uint32_t lo = 0, hi = m;                                          // first jump i with W(p_i) >= T
     while (lo < hi) {
       const uint32_t mid = (lo + hi) >> 1;
@@ -86,11 +83,9 @@ struct StepDist {
     const uint32_t i = lo;
     const int klo = i ? (int)__ldg(lst + i - 1) + 1 : 0;
     const uint32_t pi = i < m ? __ldg(lst + i) : d;
-    const int r = range(klo, (int)pi - 1, i, T);
-    uint32_t k, c;
-    if (r >= 0) { k = (uint32_t)r; c = i; }
-    else if (i < m) { k = pi; c = i + 1; }
-    else { k = d - 1; c = m; }
+    const int r = range(klo, (int)pi - 1, (int)i * da, T);
+    const uint32_t k = r >= 0 ? (uint32_t)r : (i < m ? pi : d - 1);
+    const uint32_t c = (r >= 0 || i >= m) ? i : i + 1;
     Wk = W(k, c);
     return k;
   }
@@ -100,6 +95,7 @@ struct StepDist {
 __device__ __noinline__ uint32_t replay_list(const uint32_t* __restrict__ lst, const uint32_t m, const uint32_t d,
                                              const uint32_t kp, const float fa, const float fo, const float fp,
                                              const double u) {
+  const float ub = upper_float(u);                                    // cdf < u  <=>  cdf < ub
   float cdf = 0.f;
   uint32_t k = 0, choice = d, ti = 0;
   bool kp_left = kp != NONE;
@@ -110,15 +106,43 @@ __device__ __noinline__ uint32_t replay_list(const uint32_t* __restrict__ lst, c
     if (kp_left && kp < nextp) { pos = kp; is_kp = true; }
     else if (ti < m) { pos = nextp; is_kp = false; }
     else break;
-    if (advance_run(cdf, k, pos - k, fo, u, choice)) return choice;
+    if (advance_run(cdf, k, pos - k, fo, ub, choice)) return choice;
     cdf = __fadd_rn(cdf, is_kp ? fp : fa);                            // the special element at `pos`
-    if (!((double)cdf < u)) return pos;
+    if (cdf >= ub) return pos;
     k = pos + 1;
     if (is_kp) kp_left = false;
     else { ++ti; nextp = ti < m ? __ldg(lst + ti) : NONE; }
   }
-  if (advance_run(cdf, k, d - k, fo, u, choice)) return choice;
+  if (advance_run(cdf, k, d - k, fo, ub, choice)) return choice;
   return d;                                                           // cdf[-1] < u: the reference's overflow
+}
+
+// The step after an unchecked choice == deg read (~1e-7 of the steps): prev is not joined to cur by the edge the
+// walker holds, so the step is evaluated from the rows in the reference's own order -- sequential merge, sequential
+// f32 sum and cumsum (rw/sparse_rw.py:51-91, pecanpy.py:556-557) -- with the three unweighted biases.
+__device__ __noinline__ uint32_t offedge_step(const uint32_t* __restrict__ indptr, const uint32_t* __restrict__ indices,
+                                              const float w_out, const float w_ret, const uint32_t cur,
+                                              const uint32_t prev, const double u) {
+  const uint32_t cs = indptr[cur], d = indptr[cur + 1] - cs;
+  const uint32_t ps = indptr[prev], pd = indptr[prev + 1] - ps;
+  float sum = 0.f, cdf = 0.f;
+  for (int pass = 0; pass < 2; ++pass) {
+    uint32_t i2 = 0;
+    for (uint32_t k = 0; k < d; ++k) {
+      const uint32_t x = indices[cs + k];
+      float w = w_ret;
+      if (x != prev) {
+        while (i2 < pd && indices[ps + i2] < x) ++i2;
+        w = (i2 < pd && indices[ps + i2] == x) ? 1.0f : w_out;
+      }
+      if (pass == 0) sum = __fadd_rn(sum, w);
+      else {
+        cdf = __fadd_rn(cdf, __fdiv_rn(w, sum));
+        if (!((double)cdf < u)) return k;
+      }
+    }
+  }
+  return d;
 }
 
 __device__ __forceinline__ uint32_t edge_step(const EdgeConsts& C, const uint32_t flags, const uint32_t d,
@@ -142,15 +166,17 @@ __device__ __forceinline__ uint32_t edge_step(const EdgeConsts& C, const uint32_
   bool replay = (flags & B2W_FLAG_FORCE_EXACT_REPLAY) != 0 || d > 160000u;
   uint32_t choice = d;
   if (!replay) {
-    // an upper bound of the answer from the most conservative "sure" threshold, then thresholds at that position
-    int Wk;
+    // An upper bound k_hi of the answer from the most conservative "sure" threshold and W(k) >= (k + 1) a_o - slack
+    // (slack = the downward jumps), then both thresholds with e taken at k_hi (e >= e_k for every k <= k_hi).
     const double e_row = EC * (double)(d + 2);
-    const double t_hi = ceil(A * (1.0 + e_row + 2.0 * e_row * e_row + 2.9e-14));
-    uint32_t k_hi = d - 1;
-    if (t_hi <= (double)Wd) k_hi = D.first_at_least((int)t_hi, Wk);
+    const double t_hi = A * (1.0 + e_row + 2.0 * e_row * e_row + 2.9e-14);
+    const int slack = (D.da < 0 ? (int)D.m * -D.da : 0) + (D.dr < 0 && D.kp != NONE ? -D.dr : 0);
+    const double k_up = (t_hi + (double)slack) * D.inv + 1.0;          // > ceil((t_hi + slack) / a_o) - 1
+    const uint32_t k_hi = k_up < (double)(d - 1) ? (uint32_t)k_up : d - 1;
     const double e = EC * (double)(k_hi + 3);
     const int T_poss = (int)ceil(A * (1.0 - e - 2.9e-14));
     const double t_sure = ceil(A * (1.0 + e + 2.0 * e * e + 2.9e-14));
+    int Wk;
     const uint32_t k = D.first_at_least(T_poss, Wk);                  // T_poss <= W_d: k exists, k <= k_hi
     if ((double)Wk >= t_sure) choice = k; else replay = true;
   }
@@ -168,34 +194,37 @@ __device__ __forceinline__ uint32_t edge_step(const EdgeConsts& C, const uint32_
 
 template <int MINB>
 __global__ void __launch_bounds__(EW_THREADS, MINB) walk_uw_edge_kernel(const WalkParams P, const EdgeConsts C) {
+  __shared__ uint32_t s_stage[8 * EW_THREADS];
   const uint32_t L = P.L;
   uint32_t st_steps = 0, st_replays = 0, st_overflow = 0;
   for (uint64_t i = blockIdx.x * (uint64_t)EW_THREADS + threadIdx.x; i < P.n_rows; i += (uint64_t)gridDim.x * EW_THREADS) {
-    uint32_t* const out = P.out + i * P.ld_out;
+    RowWriter<EW_THREADS> row;
+    row.begin(P.out + i * P.ld_out, s_stage);
     uint32_t cur = __ldg(P.start + i), prev = 0;
     uint32_t cs = __ldg(P.indptr + cur);
     uint32_t d = __ldg(P.indptr + cur + 1) - cs;
     uint32_t kpf = 0, toff = 0, eff = L + 1;
     bool edge_ok = true;                                              // the walker arrived over a stored edge
-    out[0] = cur;
+    row.push(0, cur);
     uint32_t j = 1;
     for (; j <= L; ++j) {
       if (d == 0) { eff = j; break; }                                 // pecanpy.py:194-196, 204-206
       const double u = step_uniform(P, i, j);
       uint32_t choice;
       if (edge_ok) choice = edge_step(C, P.flags, d, j > 1, kpf, toff, u, st_replays);
-      else choice = otf_choice_seq<false>(P, cur, true, prev, u);     // after an unchecked choice == deg read
+      else choice = offedge_step(P.indptr, P.indices, __fmul_rn(__int2float_rn(C.a_out), C.g), __fmul_rn(__int2float_rn(C.a_ret), C.g), cur, prev, u);
       if (choice == d) ++st_overflow;
       edge_ok = choice < d;
       const uint4 r = __ldg(C.rec + (cs + choice));                   // [cs + d] is the next row's first edge: pecanpy.py:559
       prev = cur;
       cur = r.x; kpf = r.y; toff = r.z; d = r.w;
-      out[j] = cur;
+      row.push(j, cur);
       cs = __ldg(P.indptr + cur);
-      ++st_steps;
     }
-    for (uint32_t z = j; z <= L; ++z) out[z] = 0u;                    // zero tail (np.zeros, pecanpy.py:182)
-    out[L + 1] = eff;
+    st_steps += eff - 1;
+    for (uint32_t z = j; z <= L; ++z) row.push(z, 0u);                // zero tail (np.zeros, pecanpy.py:182)
+    row.push(L + 1, eff);
+    row.finish(L + 2);
   }
   if (P.stats && !(P.flags & B2W_FLAG_NO_FILTER_STATS)) {
     for (int o = 16; o; o >>= 1) {
@@ -211,7 +240,94 @@ __global__ void __launch_bounds__(EW_THREADS, MINB) walk_uw_edge_kernel(const Wa
   }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// PreComp through the per-edge index.  The reference's step (pecanpy.py:427-438) bisects prev in row(cur) to find
+// the alias table of the (prev, cur) pair: that position is a property of the edge the walker arrived over and sits
+// in its record (kpf: the insertion point, exactly what np.searchsorted returns, found or not).  A step is then
+//     record (L2: 16 B x nnz)  ->  alias_indptr[cur], indptr[cur] (L2)  ->  one {q, j} entry (HBM)  ->  next record
+// instead of log2(deg) dependent probes + two table sectors.  Only the step after the first step's unchecked
+// choice == deg read (pecanpy.py:424, 559) has no edge to lean on and bisects like the reference.
+template <int MINB>
+__global__ void __launch_bounds__(EW_THREADS, MINB) walk_precomp_edge_kernel(const WalkParams P, const uint4* __restrict__ rec) {
+  __shared__ uint32_t s_stage[8 * EW_THREADS];
+  const uint32_t L = P.L;
+  unsigned long long st_steps = 0, st_overflow = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)EW_THREADS + threadIdx.x; i < P.n_rows; i += (uint64_t)gridDim.x * EW_THREADS) {
+    RowWriter<EW_THREADS> row;
+    row.begin(P.out + i * P.ld_out, s_stage);
+    const uint64_t grow = P.row0 + i;
+    uint32_t cur = __ldg(P.start + i), prev = 0;
+    uint32_t cs = __ldg(P.indptr + cur);
+    uint32_t d = __ldg(P.indptr + cur + 1) - cs;
+    uint32_t lo = 0, eff = L + 1;
+    bool edge_ok = true;
+    row.push(0, cur);
+    uint32_t j = 1;
+    for (; j <= L; ++j) {
+      if (d == 0) { eff = j; break; }                                 // pecanpy.py:194-196, 204-206
+      StepRng rng;
+      rng.begin(P.key0, P.key1, grow, j);
+      uint32_t choice;
+      if (j == 1) {
+        // first step: cumsum / searchsorted on the NON-extended first-order probabilities (pecanpy.py:412-424)
+        choice = otf_choice_seq<false>(P, cur, false, 0, rng.uniform());
+        if (choice == d) { ++st_overflow; edge_ok = false; }
+      } else {
+        if (!edge_ok) {                                               // np.searchsorted(indices[start:end], prev) (:429)
+          uint32_t a = 0, b = d;
+          while (a < b) { const uint32_t mid = (a + b) >> 1; if (__ldg(P.indices + cs + mid) < prev) a = mid + 1; else b = mid; }
+          lo = a;
+          edge_ok = true;
+        }
+        const uint64_t off = __ldg(P.alias_indptr + cur) + (uint64_t)d * lo;   // (:433-434)
+        const uint32_t kk = rng.randint(d);                           // alias_draw (:668-677)
+        const double u = rng.uniform();
+        if (P.alias_qj) {
+          const uint2 e = __ldg(P.alias_qj + off + kk);
+          choice = (u < (double)__uint_as_float(e.x)) ? kk : e.y;
+        } else {
+          choice = (u < (double)__ldg(P.alias_q + off + kk)) ? kk : __ldg(P.alias_j + off + kk);
+        }
+      }
+      const uint4 r = __ldg(rec + (cs + choice));
+      prev = cur;
+      cur = r.x; lo = r.y & KPF_POS_MASK; d = r.w;
+      row.push(j, cur);
+      cs = __ldg(P.indptr + cur);
+    }
+    st_steps += eff - 1;
+    for (uint32_t z = j; z <= L; ++z) row.push(z, 0u);                // zero tail (np.zeros, pecanpy.py:182)
+    row.push(L + 1, eff);
+    row.finish(L + 2);
+  }
+  if (P.stats && !(P.flags & B2W_FLAG_NO_FILTER_STATS)) {
+    for (int o = 16; o; o >>= 1) {
+      st_steps += __shfl_xor_sync(B2W_FULL, st_steps, o);
+      st_overflow += __shfl_xor_sync(B2W_FULL, st_overflow, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicAdd((unsigned long long*)&P.stats->steps, st_steps);
+      if (st_overflow) atomicAdd((unsigned long long*)&P.stats->overflow_choices, st_overflow);
+    }
+  }
+}
+
 }  // namespace
+
+int b2w_launch_precomp_edge(const b2w_graph* g, const WalkParams& P, cudaStream_t s) {
+  if (!(g->flags & B2W_GRAPH_HAS_EDGE_INDEX)) { b2w_set_error("walk_precomp_edge_kernel: no edge index attached"); return B2W_ERR_INVALID; }
+  const uint64_t want = (P.n_rows + EW_THREADS - 1) / EW_THREADS;
+  const uint64_t cap = (uint64_t)g->num_sms * 64;
+  unsigned blocks = (unsigned)(want < cap ? want : cap);
+  if (blocks < 1) blocks = 1;
+  const uint4* rec = reinterpret_cast<const uint4*>(g->edge_rec);
+  const int mb = (int)((P.flags >> 16) & 0xF);                        // tuning: resident CTAs per SM (0 = default)
+  if (mb == 8) walk_precomp_edge_kernel<8><<<blocks, EW_THREADS, 0, s>>>(P, rec);
+  else if (mb == 4) walk_precomp_edge_kernel<4><<<blocks, EW_THREADS, 0, s>>>(P, rec);
+  else if (mb == 5) walk_precomp_edge_kernel<5><<<blocks, EW_THREADS, 0, s>>>(P, rec);
+  else walk_precomp_edge_kernel<6><<<blocks, EW_THREADS, 0, s>>>(P, rec);
+  return b2w_cuda_fail(cudaGetLastError(), "walk_precomp_edge_kernel launch");
+}
 
 int b2w_launch_uw_edge(const b2w_graph* g, const WalkParams& P, cudaStream_t s) {
   int gexp = 0;

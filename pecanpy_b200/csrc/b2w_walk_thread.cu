@@ -12,9 +12,13 @@ namespace {
 
 // alias_draw (pecanpy.py:668-677): kk = randint(k); rand() < q[kk] ? kk : j[kk]
 __device__ __forceinline__ uint32_t alias_draw(const uint32_t* __restrict__ j, const float* __restrict__ q,
-                                               uint64_t off, uint32_t k, StepRng& rng) {
+                                               const uint2* __restrict__ qj, uint64_t off, uint32_t k, StepRng& rng) {
   uint32_t kk = rng.randint(k);
   double u = rng.uniform();
+  if (qj) {                                                          // packed table: one 8-byte entry per draw
+    const uint2 e = __ldg(qj + off + kk);
+    return (u < (double)__uint_as_float(e.x)) ? kk : e.y;
+  }
   float qv = q[off + kk];
   return (u < (double)qv) ? kk : j[off + kk];
 }
@@ -59,12 +63,12 @@ __global__ void __launch_bounds__(256, MINB) walk_thread_kernel(const WalkParams
               if (P.indices[cs + mid] < prev) lo = mid + 1; else hi = mid;
             }
             uint64_t off = P.alias_indptr[cur] + (uint64_t)deg * lo;
-            choice = alias_draw(P.alias_j, P.alias_q, off, deg, rng);
+            choice = alias_draw(P.alias_j, P.alias_q, P.alias_qj, off, deg, rng);
           }
         } else if (MODE == B2W_MODE_FIRST_ORDER_UNWEIGHTED) {
           choice = rng.randint(deg);                                   // randint(start, end) (:306-307)
         } else {                                                       // PRECOMP_FIRST_ORDER (:329-332)
-          choice = alias_draw(P.alias_j, P.alias_q, cs, deg, rng);
+          choice = alias_draw(P.alias_j, P.alias_q, nullptr, cs, deg, rng);
         }
       }
       uint32_t nxt = P.indices[cs + choice];

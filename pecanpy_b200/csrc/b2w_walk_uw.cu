@@ -53,6 +53,7 @@ __device__ __noinline__ uint32_t replay_exact(const uint32_t* __restrict__ bm, c
                                               const uint32_t nwords, const uint32_t d, const uint32_t kp, const float fa,
                                               const float fo, const float fp, const double u) {
   const Tile<G> T;
+  const float ub = upper_float(u);                                    // cdf < u  <=>  cdf < ub
   float cdf = 0.f;
   uint32_t k = 0, choice = d;
   for (uint32_t w0 = 0; w0 < nwords; w0 += G) {
@@ -68,14 +69,14 @@ __device__ __noinline__ uint32_t replay_exact(const uint32_t* __restrict__ bm, c
       while (wb) {
         const uint32_t pos = wbase + __ffs(wb) - 1;
         wb &= wb - 1;
-        if (advance_run(cdf, k, pos - k, fo, u, choice)) return choice;
+        if (advance_run(cdf, k, pos - k, fo, ub, choice)) return choice;
         cdf = __fadd_rn(cdf, pos == kp ? fp : fa);                    // the special element at `pos`
-        if (!((double)cdf < u)) return pos;
+        if (cdf >= ub) return pos;
         k = pos + 1;
       }
     }
   }
-  if (advance_run(cdf, k, d - k, fo, u, choice)) return choice;
+  if (advance_run(cdf, k, d - k, fo, ub, choice)) return choice;
   return d;                                                           // cdf[-1] < u: the reference's overflow
 }
 

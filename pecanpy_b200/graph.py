@@ -97,16 +97,24 @@ def _parse_edge_list_native(path: str, weighted: bool, delimiter: str):
                                           C.byref(nl)), "b2w_edgelist_fetch")
     finally:
         lib.b2w_edgelist_free(h)
-    for k in range(nl.value):
-        warnings.warn(f"Non-positive edge ignored: line {lines[k]}", RuntimeWarning, stacklevel=3)
+    if nl.value:
+        # the same message as the reference / the Python parser (graph.py:187-192): edge and weight of the line
+        want = {int(lines[k]) for k in range(nl.value)}
+        with open(path, encoding="utf-8", newline="\n") as f:
+            for no, line in enumerate(f, start=1):
+                if no in want:
+                    t = line.strip().split(delimiter)
+                    warnings.warn(f"Non-positive edge ignored: w({t[0].strip()},{t[1].strip()}) = {float(t[-1])}",
+                                  RuntimeWarning, stacklevel=3)
     names = blob.raw[:max(int(nb.value) - 1, 0)].decode("ascii").split("\0") if n.value else []
     return names, src.astype(np.int64), dst.astype(np.int64), w
 
 
 def _parse_edge_list_python(path: str, weighted: bool, delimiter: str = "\t"):
     """The same parse in NumPy-vectorised Python (Unicode aware; used when the native parser is unavailable)."""
-    with open(path, encoding="utf-8") as f:
-        lines = f.read().splitlines()
+    with open(path, encoding="utf-8") as f:                 # universal newlines, as the reference's `for line in f`
+        lines = f.read().split("\n")                        # (str.splitlines would also break at \x0b, \x1c, \x85, ...)
+    # blank lines are skipped (the reference raises IndexError on them, graph.py:166-167: a documented tolerance)
     lines = [ln for ln in lines if ln.strip()]
     if not lines:
         return [], np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.float64)

@@ -1,9 +1,40 @@
-"""b2w_csr_from_edges (device CSR build) against the reference's ingest conventions (graph.py:160-341): dict of
-dicts filled line by line -- later lines overwrite -- rows emitted with sorted columns."""
+"""b2w_csr_from_edges (device CSR build) against the UNMODIFIED reference's ingest (graph.py:160-341: dict of dicts
+filled line by line -- later lines overwrite -- rows emitted with sorted columns): the fixtures
+tests/golden/graph_*.npz hold edge-list texts and the arrays the reference's AdjlstGraph.read / to_csr made of them
+(oracle/gen_golden_graph.py).  The random multigraphs further down use a restatement of add_edge + to_csr on
+integer endpoints as an additional, larger check."""
+import glob
+import os
+import warnings
+
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GRAPH_FIXTURES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "graph_*.npz"))
+                        if "literals" not in f)
+
+
+@pytest.mark.parametrize("name", GRAPH_FIXTURES)
+def test_read_edg_on_device_equals_reference(tmp_path, name):
+    """read_edg(device=...) = native parser + b2w_csr_from_edges: nodes and CSR arrays byte-identical to what the
+    reference built from the same file."""
+    from pecanpy_b200.graph import SparseGraph
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    path = tmp_path / (name + ".edg")
+    with open(path, "w", newline="", encoding="utf-8") as f:
+        f.write(str(z["text"]))
+    g = SparseGraph()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        g.read_edg(str(path), weighted=bool(z["weighted"]), directed=bool(z["directed"]), delimiter=str(z["delimiter"]),
+                   device="cuda:0")
+    assert g.nodes == [str(x) for x in z["nodes"]]
+    for k in ("indptr", "indices", "data"):
+        got = getattr(g, k)
+        assert got.dtype == z[k].dtype and np.array_equal(got, z[k]), k
 
 
 def _reference_csr(n, src, dst, w, directed):

@@ -1,5 +1,10 @@
-"""Host-side containers: the input layout the kernels consume (reference graph.py conventions)."""
+"""Host-side containers and ingest against the UNMODIFIED reference: tests/golden/graph_*.npz hold the text of
+edge-list files and what the reference's AdjlstGraph.read / to_csr / to_dense / read_edg / from_mat
+(graph.py:160-362, 423-528, 587-657) made of them (written by oracle/gen_golden_graph.py, which imports the
+reference in the build container)."""
+import glob
 import os
+import warnings
 
 import numpy as np
 import pytest
@@ -7,64 +12,131 @@ import pytest
 from pecanpy_b200.graph import DenseGraph, SparseGraph
 
 KARATE = "/root/reference/demo/karate.edg"
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GRAPH_FIXTURES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "graph_*.npz"))
+                        if "literals" not in f)
 
 
-def _reference_style_parse(path, weighted, directed, delimiter="\t"):
-    """Straightforward restatement of AdjlstGraph.read + to_csr (graph.py:217-341): dict of dicts."""
-    ids, data = {}, []
-    for line in open(path):
-        t = line.strip().split(delimiter)
-        if not line.strip():
-            continue
-        a, b = t[0].strip(), t[1].strip()
-        w = float(t[-1]) if weighted else 1.0
-        if w <= 0:
-            continue
-        for x in (a, b):
-            if x not in ids:
-                ids[x] = len(ids); data.append({})
-        data[ids[a]][ids[b]] = w
-        if not directed:
-            data[ids[b]][ids[a]] = w
-    indptr = np.zeros(len(ids) + 1, np.uint32)
-    idx, dat = [], []
-    for i, row in enumerate(data):
-        indptr[i + 1] = indptr[i] + len(row)
-        for j in sorted(row):
-            idx.append(j); dat.append(row[j])
-    names = [None] * len(ids)
-    for k, v in ids.items():
-        names[v] = k
-    return names, indptr, np.array(idx, np.uint32), np.array(dat, np.float32)
+def load_graph_fixture(name, tmp_path):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    c = {k: z[k] for k in z.files}
+    path = tmp_path / (name + ".edg")
+    with open(path, "w", newline="", encoding="utf-8") as f:
+        f.write(str(c["text"]))
+    c["path"] = str(path)
+    c["weighted"], c["directed"], c["delimiter"] = bool(c["weighted"]), bool(c["directed"]), str(c["delimiter"])
+    c["nodes"] = [str(x) for x in c["nodes"]]
+    return c
 
 
-@pytest.mark.parametrize("directed", [False, True])
-@pytest.mark.parametrize("weighted", [False, True])
-def test_read_edg_matches_reference_conventions(tmp_path, weighted, directed):
-    rng = np.random.default_rng(3)
-    path = tmp_path / "g.edg"
-    with open(path, "w") as f:
-        for _ in range(400):
-            a, b = rng.integers(0, 40, size=2)
-            w = rng.choice([0.5, 1.5, 2.0, -1.0, 0.0])
-            f.write(f"n{a}\tn{b}\t{w}\n" if weighted else f"n{a}\tn{b}\n")
+def test_fixtures_exist():
+    assert len(GRAPH_FIXTURES) >= 9
+
+
+@pytest.mark.parametrize("name", GRAPH_FIXTURES)
+def test_read_edg_equals_reference(tmp_path, name):
+    """SparseGraph / DenseGraph.read_edg (native parser + host CSR build) == the reference's, byte for byte:
+    duplicates and both orientations (later line wins), self loops, weights <= 0 dropped without registering their
+    ids, ids stripped, CRLF, extra columns, no trailing newline, other delimiters."""
+    c = load_graph_fixture(name, tmp_path)
     g = SparseGraph()
-    import warnings
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        g.read_edg(str(path), weighted=weighted, directed=directed)
-    names, indptr, indices, data = _reference_style_parse(str(path), weighted, directed)
-    assert g.nodes == names
-    assert np.array_equal(g.indptr, indptr) and np.array_equal(g.indices, indices) and np.array_equal(g.data, data)
-    assert g.indptr.dtype == np.uint32 and g.indices.dtype == np.uint32 and g.data.dtype == np.float32
+        g.read_edg(c["path"], weighted=c["weighted"], directed=c["directed"], delimiter=c["delimiter"])
+    assert g.nodes == c["nodes"]
+    for k in ("indptr", "indices", "data"):
+        got = getattr(g, k)
+        assert got.dtype == c[k].dtype and np.array_equal(got, c[k]), k
+    assert g.num_edges == int(c["num_edges"])
     d = DenseGraph()
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
-        d.read_edg(str(path), weighted=weighted, directed=directed)
-    dense = np.zeros((len(names), len(names)))
-    for i in range(len(names)):
-        dense[i, indices[indptr[i]:indptr[i + 1]]] = data[indptr[i]:indptr[i + 1]]
-    assert np.array_equal(d.data, dense) and np.array_equal(d.nonzero, dense != 0) and d.data.dtype == np.float64
+        d.read_edg(c["path"], weighted=c["weighted"], directed=c["directed"], delimiter=c["delimiter"])
+    assert d.nodes == c["nodes"]
+    assert d.data.dtype == c["dense"].dtype and np.array_equal(d.data, c["dense"])
+    assert np.array_equal(d.nonzero, c["nonzero"])
+
+
+@pytest.mark.parametrize("name", GRAPH_FIXTURES)
+def test_both_parsers_equal_reference(tmp_path, name, monkeypatch):
+    """The native (C) parser and the Python fallback feed the same CSR build: both must reproduce the reference."""
+    from pecanpy_b200 import graph as G
+    c = load_graph_fixture(name, tmp_path)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        nat = G._parse_edge_list_native(c["path"], c["weighted"], c["delimiter"])
+        py = G._parse_edge_list_python(c["path"], c["weighted"], c["delimiter"])
+    assert nat is not None, "libb2w.so must be built for this test"
+    assert nat[0] == py[0] == c["nodes"]
+    for x, y in zip(nat[1:], py[1:]):
+        assert np.array_equal(x, y)
+    monkeypatch.setattr(G, "_parse_edge_list_native", lambda *a, **k: None)     # force the fallback through read_edg
+    g = SparseGraph()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        g.read_edg(c["path"], weighted=c["weighted"], directed=c["directed"], delimiter=c["delimiter"])
+    assert g.nodes == c["nodes"]
+    assert np.array_equal(g.indptr, c["indptr"]) and np.array_equal(g.indices, c["indices"]) and np.array_equal(g.data, c["data"])
+
+
+def test_dropped_edge_warning_is_the_reference_message(tmp_path):
+    """graph.py:184-192: 'Non-positive edge ignored: w(id1,id2) = weight' from either parser."""
+    from pecanpy_b200 import graph as G
+    p = tmp_path / "d.edg"
+    p.write_text("a\tb\t-1\n x \tc\t0\nb\tc\t2\n")
+    for parse in (G._parse_edge_list_native, G._parse_edge_list_python):
+        with warnings.catch_warnings(record=True) as rec:
+            warnings.simplefilter("always")
+            names, *_ = parse(str(p), True, "\t")
+        assert names == ["b", "c"]
+        assert [str(r.message) for r in rec] == ["Non-positive edge ignored: w(a,b) = -1.0",
+                                                 "Non-positive edge ignored: w(x,c) = 0.0"]
+
+
+def test_native_parser_leaves_ambiguous_inputs_to_python(tmp_path):
+    """NUL bytes, bare CR line ends, '_' / '(' in a weight: the byte-level parser steps aside (B2W_ERR_UNSUPPORTED)
+    and read_edg gives what Python's text-mode read + float() give."""
+    from pecanpy_b200 import graph as G
+    cases = {"nul.edg": ("a\x00b\tc\nc\td\n", False), "cr.edg": ("a\tb\rb\tc\r", False),
+             "under.edg": ("a\tb\t1_0\n", True)}
+    for fn, (text, weighted) in cases.items():
+        p = tmp_path / fn
+        with open(p, "w", newline="") as f:
+            f.write(text)
+        assert G._parse_edge_list_native(str(p), weighted, "\t") is None, fn
+    g = SparseGraph()
+    g.read_edg(str(tmp_path / "cr.edg"), weighted=False, directed=True)
+    assert g.nodes == ["a", "b", "c"] and g.num_edges == 2
+    g.read_edg(str(tmp_path / "under.edg"), weighted=True, directed=True)
+    assert g.data.tolist() == [10.0]
+    g.read_edg(str(tmp_path / "nul.edg"), weighted=False, directed=True)
+    assert g.nodes == ["a\x00b", "c", "d"]
+    bad = tmp_path / "nanp.edg"
+    bad.write_text("a\tb\tnan(123)\n")
+    with pytest.raises(ValueError):
+        g.read_edg(str(bad), weighted=True, directed=True)
+    # a line separator that only str.splitlines() honours must not split a line (the reference iterates the file)
+    sep = tmp_path / "sep.edg"
+    sep.write_text("a\x1cb\tc\n")
+    g.read_edg(str(sep), weighted=False, directed=True)
+    assert g.nodes == ["a\x1cb", "c"]
+    assert G._parse_edge_list_python(str(sep), False, "\t")[0] == ["a\x1cb", "c"]
+
+
+def test_from_mat_equals_reference_literals():
+    """The matrices and CSR literals of the reference's test/test_graph.py:16-78 through from_mat."""
+    z = np.load(os.path.join(GOLDEN, "graph_testgraph_literals.npz"))
+    for i in (1, 2, 3):
+        ids = [str(x) for x in z[f"ids{i}"]]
+        sp = SparseGraph.from_mat(z[f"mat{i}"], ids)
+        assert sp.nodes == ids
+        for k in ("indptr", "indices", "data"):
+            assert getattr(sp, k).dtype == z[f"{k}{i}"].dtype and np.array_equal(getattr(sp, k), z[f"{k}{i}"])
+        assert sp.num_edges == int(z[f"num_edges{i}"]) and sp.density == float(z[f"density{i}"])
+        dn = DenseGraph.from_mat(z[f"mat{i}"], ids)
+        assert np.array_equal(dn.data, z[f"dense{i}"]) and dn.data.dtype == z[f"dense{i}"].dtype
+        assert np.array_equal(dn.nonzero, z[f"nonzero{i}"])
+        assert dn.num_edges == int(z[f"num_edges{i}"])
 
 
 @pytest.mark.skipif(not os.path.exists(KARATE), reason="reference demo file only exists in the build container")
