@@ -1,21 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- walk-steps/s of the B200 walk engine on the BASELINE.json workloads.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl ours|reference] [--no-extra]
 
 One "step" = one pass of the hot path (Base._random_walks, reference pecanpy.py:164-210) over the
 whole job: num_walks x num_nodes walkers x walk_length steps.  Default workload = BASELINE config #3
 (the configuration the north-star target is quoted on): synthetic power-law graph, 1M nodes / 10M
 edges, SparseOTF p=4 q=0.25, 10 x 80.  With N > 1 (torchrun, one rank per GPU) the graph is replicated,
-the shuffled start array is sharded into N contiguous row blocks, each rank walks its block into its
-slice of the full matrix and ONE NCCL all-gather collects it ("scaling": "strong": the job is fixed).
+the shuffled start array is sharded over the ranks and every rank ends with the whole walk matrix:
+the rows are walked in a few batches and each batch is all-gathered (NCCL over NVLink) while the next one
+is being walked ("scaling": "strong": the job is fixed).
 
 Prints ONE JSON line (rank 0).  `value` = steps of the whole job / device time (max over ranks),
-inputs resident in HBM.  `e2e` = the same through the host-buffer C-ABI call (b2w_walk_host): start
-nodes in pinned host memory, walk matrix delivered to pinned host memory, copies inside the timed
-region.  `roofline` = algorithmic HBM bytes of the walk kernel / its CUDA-event time,
-against the measured copy bandwidth in MEASURED_PEAKS.json.  `cpu_baseline` = the C port of the
-reference's algorithm (oracle/walk_oracle.c, OpenMP over walkers) on the host cores, bounded sample.
+inputs resident in HBM.  `e2e` = the same through the host-buffer C-ABI call (b2w_walk_host; at N > 1
+b2w_walk_multi from ONE process over the N GPUs): start nodes in pinned host memory, ONE walk matrix
+delivered to pinned host memory, copies inside the timed region.  `roofline` = algorithmic HBM bytes of
+the walk kernel / its CUDA-event time, against the measured copy bandwidth in
+MEASURED_PEAKS.json; `roofline.dram_frac` = the kernel's real DRAM traffic (ncu, profiles/traffic.json)
+on the same scale.  `cpu_baseline` = the C port of the reference's algorithm (oracle/walk_oracle.c, OpenMP
+over walkers) on the host cores, bounded sample.  `extra` (N = 1, default workload): the same measurements
+for the other BASELINE configurations (#2 ER, #4 PreComp, #5 DenseOTF node2vec+) and for the weighted /
+node2vec+ SparseOTF kernels, each a short sub-benchmark with its own roofline, cpu_baseline, e2e and clocks.
 
 --impl reference: the CPU arm on the same workload/metric (rank 0 only).
 """
@@ -36,20 +41,28 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (mode, p, q, extend, gamma, weighted, generator, n, m, num_walks, L)
     "powerlaw-1M-10M-sparseotf": dict(mode="SparseOTF", p=4.0, q=0.25, extend=False, gen="powerlaw", n=1_000_000,
-                                      m=10_000_000, weighted=False, num_walks=10, L=80, seed=1),
+                                      m=10_000_000, weighted=False, num_walks=10, L=80, seed=1, config="#3"),
     "powerlaw-1M-10M-sparseotf-weighted": dict(mode="SparseOTF", p=4.0, q=0.25, extend=False, gen="powerlaw",
-                                               n=1_000_000, m=10_000_000, weighted=True, num_walks=10, L=80, seed=1),
+                                               n=1_000_000, m=10_000_000, weighted=True, num_walks=10, L=80, seed=1,
+                                               config="#3 topology, random weights (generic kernel)"),
+    "powerlaw-1M-10M-sparseotf-n2vplus": dict(mode="SparseOTF", p=4.0, q=0.25, extend=True, gamma=0.0, gen="powerlaw",
+                                              n=1_000_000, m=10_000_000, weighted=True, num_walks=10, L=80, seed=1,
+                                              config="#3 topology, random weights, node2vec+ (--extend)"),
     "er-100k-1M-sparseotf": dict(mode="SparseOTF", p=0.5, q=2.0, extend=False, gen="er", n=100_000, m=1_000_000,
-                                 weighted=False, num_walks=10, L=80, seed=0),
+                                 weighted=False, num_walks=10, L=80, seed=0, config="#2"),
     "er-50k-1M-precomp": dict(mode="PreComp", p=0.25, q=4.0, extend=False, gen="er", n=50_000, m=1_000_000,
-                              weighted=True, num_walks=10, L=80, seed=2),
-    "dense-20k-denseotf-n2vplus": dict(mode="DenseOTF", p=0.5, q=2.0, extend=True, gen="dense", n=20_000, m=0,
-                                       weighted=True, num_walks=10, L=80, seed=3, density=0.3),
+                              weighted=True, num_walks=10, L=80, seed=2, config="#4"),
+    "dense-20k-denseotf-n2vplus": dict(mode="DenseOTF", p=0.5, q=2.0, extend=True, gamma=0.0, gen="dense", n=20_000, m=0,
+                                       weighted=True, num_walks=10, L=80, seed=3, density=0.3, config="#5"),
 }
 DEFAULT_WORKLOAD = "powerlaw-1M-10M-sparseotf"
+# sub-benchmarks appended to the default N = 1 line: (workload, warm-up passes, minimum timed passes)
+EXTRA = [("er-100k-1M-sparseotf", 3, 5), ("er-50k-1M-precomp", 3, 5), ("dense-20k-denseotf-n2vplus", 3, 2),
+         ("powerlaw-1M-10M-sparseotf-weighted", 3, 2), ("powerlaw-1M-10M-sparseotf-n2vplus", 3, 2)]
 METRIC = "walk-steps/s"
+CHECK_SEED = 12345          # the pass whose matrix is checksummed: the same for every N, K, W
+MIN_TIMED_S = 1.0           # sub-benchmarks: a timed region shorter than this is repeated
 
 
 def log(*a):
@@ -91,15 +104,16 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, period_ms: int = 20):
         self.idx = gpu_index
+        self.period = period_ms
         self.proc = None
         self.lines = []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", str(self.period), "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -108,11 +122,20 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self) -> dict:
+    def wait_first(self, timeout=3.0):
+        """nvidia-smi needs a moment to start: do not open the timed region before its first sample."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def samples_since(self, t0: float) -> int:
+        return sum(1 for t, _ in self.lines if t >= t0)
+
+    def stop(self, t0: float = 0.0, t1: float = float("inf")) -> dict:
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -120,7 +143,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for t, ln in self.lines:
+            if not (t0 <= t <= t1 + 0.05):
+                continue                                    # only samples taken during the timed region
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -136,9 +161,11 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ bytes
-def algorithmic_bytes_sparse_gpu(torch, deg_t, walks_t, L: int) -> int:
+def algorithmic_bytes_sparse_gpu(torch, deg_t, walks_t, L: int, extend: bool = False) -> int:
     """SURVEY.md 8d, SparseOTF node2vec: step 1: 12 + 8 d_cur; step j>=2: 20 + 8 d_cur + 4 d_prev;
-    + 4 per walker (start).  Evaluated exactly from the walk matrix, on the device, in row chunks."""
+    + 4 per walker (start).  node2vec+: + 4 d_prev (weights of row(prev)) + 4 (thr[cur]) per step j>=2 (the 4 c
+    threshold gathers of the c common neighbours are not counted: a lower bound).  Evaluated exactly from the walk
+    matrix, on the device, in row chunks."""
     total = 0
     rows = walks_t.shape[0]
     chunk = 1 << 19
@@ -150,8 +177,8 @@ def algorithmic_bytes_sparse_gpu(torch, deg_t, walks_t, L: int) -> int:
         d = deg_t[w[:, :L].to(torch.int64)]
         cur_ok = cols < nsteps[:, None]                 # entry c is `cur` of step c + 1
         prev_ok = cols < (nsteps[:, None] - 1)          # entry c is `prev` of step c + 2
-        total += int((8 * (d * cur_ok).sum() + 4 * (d * prev_ok).sum()).item())
-        total += int((12 * (nsteps >= 1).sum() + 20 * torch.clamp(nsteps - 1, min=0).sum()).item())
+        total += int((8 * (d * cur_ok).sum() + (8 if extend else 4) * (d * prev_ok).sum()).item())
+        total += int((12 * (nsteps >= 1).sum() + (24 if extend else 20) * torch.clamp(nsteps - 1, min=0).sum()).item())
         total += 4 * w.shape[0]
     return total
 
@@ -173,39 +200,55 @@ def algorithmic_bytes_precomp(torch, deg_t, walks_t, L: int) -> int:
     return total
 
 
+def matrix_checksum(torch, walks_t) -> str:
+    """Order-sensitive 64-bit checksum of a device walk matrix (wrap-around int64 arithmetic): equal for equal
+    matrices whatever the number of GPUs that produced them."""
+    acc = 0
+    rows, ld = walks_t.shape
+    chunk = 1 << 19
+    for r0 in range(0, rows, chunk):
+        w = walks_t[r0:r0 + chunk].to(torch.int64) & 0xFFFFFFFF
+        idx = (torch.arange(r0, r0 + w.shape[0], device=w.device, dtype=torch.int64)[:, None] * ld +
+               torch.arange(ld, device=w.device, dtype=torch.int64)[None, :])
+        acc = (acc + int(((w + 1) * ((idx * 0x9E3779B1) % 0x7FFFFFFF + 1)).sum().item())) & 0xFFFFFFFFFFFFFFFF
+    return f"{acc:016x}"
+
+
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_port_rate(wl, g, start, L, budget_s: float, seed: int):
-    """Time the C port of the reference on a bounded sample; returns (steps/s, cores, sample description)."""
+def cpu_walk(wl, g, start, L, seed, cores):
     from oracle import oracle as orc
+    if g["kind"] == "dense":
+        return orc.walk_dense(g["data"], g["nonzero"], wl["p"], wl["q"], start, L, extend=wl["extend"],
+                              thr=g.get("thr"), rng=orc.RNG_PHILOX, seed=seed, nthreads=cores)
+    return orc.walk_csr(wl["mode"], g["indptr"], g["indices"], g["data"], wl["p"], wl["q"], start, L,
+                        extend=wl["extend"], thr=g.get("thr"), alias=g.get("alias"), rng=orc.RNG_PHILOX, seed=seed,
+                        nthreads=cores)
+
+
+def cpu_port_rate(wl, g, start, L, budget_s: float, seed: int):
+    """Time the C port of the reference on a bounded sample; returns (steps/s, cores, sample description, rows)."""
     cores = host_threads()
 
-    def run(rows):
+    def run(rows, nt):
         t0 = time.perf_counter()
-        if g["kind"] == "dense":
-            out = orc.walk_dense(g["data"], g["nonzero"], wl["p"], wl["q"], start[:rows], L, extend=wl["extend"],
-                                 thr=g.get("thr"), rng=orc.RNG_PHILOX, seed=seed, nthreads=cores)
-        else:
-            out = orc.walk_csr(wl["mode"], g["indptr"], g["indices"], g["data"], wl["p"], wl["q"], start[:rows], L,
-                               extend=wl["extend"], thr=g.get("thr"), alias=g.get("alias"), rng=orc.RNG_PHILOX, seed=seed,
-                               nthreads=cores)
+        out = cpu_walk(wl, g, start[:rows], L, seed, nt)
         dt = time.perf_counter() - t0
         return int((out[:, -1].astype(np.int64) - 1).sum()), dt
 
     # thread count: all hardware threads, or one per physical core if that is faster (SMT often hurts this
     # latency-bound gather loop); a short probe decides
     rows = min(start.size, 40000 if g["kind"] != "dense" else 512)
-    run(rows)                                               # warm-up (thread pool, page faults, clocks)
+    run(rows, cores)                                        # warm-up (thread pool, page faults, clocks)
     cores_all, half = cores, max(1, cores // 2)
     best = {}
     for nt in (cores_all, half, cores_all, half):
-        cores = nt
-        s_, dt_ = run(rows)
+        s_, dt_ = run(rows, nt)
         best[nt] = max(best.get(nt, 0.0), s_ / dt_)
     cores = cores_all if best[cores_all] >= best[half] else half
     # grow the sample until it runs for at least ~40% of the budget (a tiny probe is a poor predictor),
     # capped by the budget and by the job size
     while True:
-        s, dt = run(rows)
+        s, dt = run(rows, cores)
         if dt >= 0.4 * budget_s or rows >= start.size:
             break
         rate = s / max(dt, 1e-9)
@@ -216,83 +259,23 @@ def cpu_port_rate(wl, g, start, L, budget_s: float, seed: int):
     return s / dt, cores, f"first {rows} rows of the shuffled start array x {L} steps ({s} steps in {dt:.2f}s)", rows
 
 
-# ------------------------------------------------------------------------------------------ main
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (debug only; invalidates the number)")
-    ap.add_argument("--num-walks", type=int, default=0)
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--flags", type=int, default=0, help="b2w_walk flags (debug)")
-    args = ap.parse_args()
+# ------------------------------------------------------------------------------------------ one workload, our arm
+def run_workload(name, args, K, W, rank, world, local_rank, *, do_e2e=True, do_cpu=True, cpu_budget=15.0,
+                 min_timed_s=0.0):
+    import torch
+    import torch.distributed as dist
+    from pecanpy_b200 import synth
+    from pecanpy_b200.engine import WalkEngine
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    wl = dict(WORKLOADS[args.workload])
+    dev = torch.device("cuda", local_rank)
+    wl = dict(WORKLOADS[name])
     if args.num_walks:
         wl["num_walks"] = args.num_walks
     L = wl["L"]
-    K, W = args.steps, max(args.warmup, 0)
-
-    # ---------------- reference arm: CPU port on rank 0 only
-    if args.impl == "reference":
-        if rank != 0:
-            return 0
-        g = make_graph(wl, args.scale, 0, lambda: None)
-        prep_reference_extras(wl, g)
-        from pecanpy_b200 import synth
-        start = synth.shuffled_start(g["n"], wl["num_walks"], 0)
-        per_step_budget = max(2.0, 150.0 / max(K + W, 1))
-        rate0, cores, _, rows = cpu_port_rate(wl, g, start, L, per_step_budget, seed=0)
-        times, steps = [], 0
-        from oracle import oracle as orc
-        for it in range(W + K):
-            t0 = time.perf_counter()
-            if g["kind"] == "dense":
-                out = orc.walk_dense(g["data"], g["nonzero"], wl["p"], wl["q"], start[:rows], L, extend=wl["extend"],
-                                     thr=g.get("thr"), rng=orc.RNG_PHILOX, seed=it, nthreads=cores)
-            else:
-                out = orc.walk_csr(wl["mode"], g["indptr"], g["indices"], g["data"], wl["p"], wl["q"], start[:rows], L,
-                                   extend=wl["extend"], thr=g.get("thr"), alias=g.get("alias"), rng=orc.RNG_PHILOX, seed=it,
-                                   nthreads=cores)
-            dt = time.perf_counter() - t0
-            if it >= W:
-                times.append(dt)
-                steps += int((out[:, -1].astype(np.int64) - 1).sum())
-        value = steps / sum(times)
-        sample = f"each step = first {rows} rows of the shuffled start array x {L} steps"
-        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus,
-                "steps": K, "warmup": W, "ms_per_step": 1e3 * sum(times) / max(K, 1), "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": dtype_of(wl), "data": "synthetic",
-                "config": config_of(args, wl, g, world=1),
-                "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
-                "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
-        return 0
-
-    # ---------------- our arm
-    import torch
-    import torch.distributed as dist
-    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
-
-    from pecanpy_b200 import _capi as capi
-    from pecanpy_b200 import synth
-    from pecanpy_b200.engine import WalkEngine
 
     g = make_graph(wl, args.scale, rank, barrier)
     n = g["n"]
@@ -317,22 +300,40 @@ def main():
 
     start = synth.shuffled_start(n, wl["num_walks"], 0)
     tot = start.size
-    R = (tot + world - 1) // world                     # rows per rank (last block padded)
-    tot_pad = R * world
-    lo, hi = rank * R, min(tot, (rank + 1) * R)
-    my_rows = max(hi - lo, 0)
     ld = L + 2
+    # Row blocks.  One GPU: the whole array.  N GPUs: NB batches; batch b of rank r = rows [(b N + r) B, +B), so that
+    # the all-gather of batch b fills the contiguous rows [b N B, (b + 1) N B) while batch b + 1 is being walked.
+    NB = 1 if world == 1 else max(1, min(args.batches, (tot + world * 65536 - 1) // (world * 65536)))
+    B = (tot + world * NB - 1) // (world * NB)
+    tot_pad = B * world * NB
     full = torch.zeros((tot_pad, ld), dtype=torch.int32, device=dev)
-    mine = full[rank * R:(rank + 1) * R]
-    d_start = torch.from_numpy(start[lo:hi].view(np.int32)).to(dev)
+    start_pad = np.zeros(tot_pad, dtype=np.uint32)
+    start_pad[:tot] = start
+    d_start_all = torch.from_numpy(start_pad.view(np.int32)).to(dev)
+    blocks = []                                             # (row0, rows actually walked) of this rank, per batch
+    for b in range(NB):
+        r0 = (b * world + rank) * B
+        blocks.append((r0, max(0, min(B, tot - r0))))
+    my_rows = sum(r for _, r in blocks)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > L2 (126 MB)
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
 
-    def one_pass(seed):
-        if my_rows:
-            eng.walk(wl["mode"], wl["p"], wl["q"], d_start, L, seed=seed, extend=wl["extend"], row0=lo,
-                     out=mine, flags=args.flags, collect_stats=False)
+    def one_pass(seed, events=None):
+        """Walk this rank's blocks; with N > 1 all-gather each batch on a side stream while the next one is walked."""
+        cur = torch.cuda.current_stream(dev)
+        for b, (r0, rows) in enumerate(blocks):
+            if rows:
+                eng.walk(wl["mode"], wl["p"], wl["q"], d_start_all[r0:r0 + rows], L, seed=seed, extend=wl["extend"],
+                         row0=r0, out=full[r0:r0 + rows], flags=args.flags, collect_stats=False)
+            if world > 1:
+                comm.wait_stream(cur)
+                with torch.cuda.stream(comm):
+                    seg = full[b * world * B:(b + 1) * world * B]
+                    dist.all_gather_into_tensor(seg.view(-1), full[(b * world + rank) * B:(b * world + rank + 1) * B].view(-1))
+        if events is not None:
+            events[1].record(cur)                           # this rank's walk kernels are done
         if world > 1:
-            dist.all_gather_into_tensor(full.view(-1), mine.reshape(-1))
+            cur.wait_stream(comm)
 
     for it in range(W):
         one_pass(1000 + it)
@@ -345,24 +346,38 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
-           torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        sampler.wait_first()
     torch.cuda.synchronize()
     barrier()
-    for it in range(K):
-        flush.fill_(it & 0xFF)                          # evict L2 between timed iterations (untimed)
-        e0, e1, e2 = ev[it]
-        e0.record()
-        if my_rows:
-            eng.walk(wl["mode"], wl["p"], wl["q"], d_start, L, seed=it, extend=wl["extend"], row0=lo, out=mine,
-                     flags=args.flags, collect_stats=False)
-        e1.record()
-        if world > 1:
-            dist.all_gather_into_tensor(full.view(-1), mine.reshape(-1))
-        e2.record()
+    # timed region: EXACTLY K passes for the headline (min_timed_s = 0; clocks are sampled every 20 ms).  The `extra`
+    # sub-benchmarks pass min_timed_s > 0: their K is a minimum and a region shorter than that (a 1 ms PreComp pass)
+    # is extended so that the sampler sees the GPU under load -- the number of passes actually timed is reported
+    ev = []
+    t_wall0 = time.perf_counter()
+    it = 0
+    while True:
+        flush.fill_(it & 0xFF)                              # evict L2 between timed iterations (untimed)
+        e = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+             torch.cuda.Event(enable_timing=True))
+        e[0].record()
+        one_pass(it, e)
+        e[2].record()
+        ev.append(e)
+        it += 1
+        if it >= K:
+            if it % 4 == 0 or it == K:                      # decide together (the loop must end on every rank at once)
+                torch.cuda.synchronize()
+                done = torch.tensor([1 if (time.perf_counter() - t_wall0 >= min_timed_s or it >= 400 * max(K, 1)) else 0],
+                                    device=dev)
+                if world > 1:
+                    dist.all_reduce(done, op=dist.ReduceOp.MIN)
+                if int(done.item()):
+                    break
     torch.cuda.synchronize()
+    t_wall1 = time.perf_counter()
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    K_eff = len(ev)
     t_total = sum(a.elapsed_time(c) for a, b, c in ev) * 1e-3
     t_kernel = sum(a.elapsed_time(b) for a, b, c in ev) * 1e-3
     tt = torch.tensor([t_total, t_kernel], dtype=torch.float64, device=dev)
@@ -370,17 +385,21 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_total, t_kernel_max = float(tt[0]), float(tt[1])
 
-    # kernel-side counters of one extra (untimed) pass: exact replays, reference-overflow choices
+    # one extra (untimed) pass with a fixed seed: checksum of the whole matrix (identical for every N), kernel-side
+    # counters of this rank's share
+    one_pass(CHECK_SEED)
+    torch.cuda.synchronize()
+    steps_job = eng.count_steps(full[:tot], L) if world > 1 else eng.count_steps(full[:tot], L)
+    checksum = matrix_checksum(torch, full[:tot]) if rank == 0 else None
     walk_stats = None
-    if my_rows and rank == 0:
-        eng.walk(wl["mode"], wl["p"], wl["q"], d_start, L, seed=K - 1 if K else 0, extend=wl["extend"], row0=lo,
-                 out=mine, flags=args.flags, collect_stats=True)
+    if rank == 0 and blocks[0][1]:
+        r0, rows = blocks[0]
+        eng.walk(wl["mode"], wl["p"], wl["q"], d_start_all[r0:r0 + rows], L, seed=CHECK_SEED, extend=wl["extend"], row0=r0,
+                 out=full[r0:r0 + rows], flags=args.flags, collect_stats=True)
         walk_stats = eng.stats()
-
-    # steps of the whole job, from the last timed pass (every rank holds the full matrix when world > 1)
-    steps_job = eng.count_steps(full[:tot] if world > 1 else mine[:my_rows], L)
-    steps_mine = eng.count_steps(mine[:my_rows], L) if my_rows else 0
-    value = steps_job * K / t_total
+        walk_stats["rows"] = rows
+    steps_mine = sum(eng.count_steps(full[r0:r0 + rows], L) for r0, rows in blocks if rows)
+    value = steps_job * K_eff / t_total
 
     # roofline of the walk kernel on this rank (rank 0 reports)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -389,73 +408,231 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     roofline = None
+    kname = eng.kernel_name(wl["mode"], wl["p"], wl["q"], wl["extend"], args.flags)
     if rank == 0 and my_rows:
-        kernel_s = t_kernel / K                         # this rank's own kernel time per launch
+        kernel_s = t_kernel / K_eff                     # this rank's own kernel time per pass
+        mine = torch.cat([full[r0:r0 + rows] for r0, rows in blocks if rows]) if len(blocks) > 1 else full[:my_rows]
         if g["kind"] == "csr":
             deg_t = torch.from_numpy((g["indptr"][1:].astype(np.int64) - g["indptr"][:-1].astype(np.int64))).to(dev)
             if wl["mode"] == "PreComp":
-                alg = algorithmic_bytes_precomp(torch, deg_t, mine[:my_rows], L)
+                alg = algorithmic_bytes_precomp(torch, deg_t, mine, L)
                 formula = "PreComp: 32 + 4(ceil(log2 d_cur)+1) per step j>=2; 12 + 8 d_cur step 1; 4 per walker"
             else:
-                alg = algorithmic_bytes_sparse_gpu(torch, deg_t, mine[:my_rows], L)
-                formula = "SparseOTF: 20 + 8 d_cur + 4 d_prev per step j>=2; 12 + 8 d_cur step 1; 4 per walker"
+                alg = algorithmic_bytes_sparse_gpu(torch, deg_t, mine, L, wl["extend"])
+                formula = ("SparseOTF: 20 + 8 d_cur + 4 d_prev per step j>=2; 12 + 8 d_cur step 1; 4 per walker" +
+                           ("; node2vec+: + 4 d_prev + 4 per step j>=2 (thr gathers of common neighbours not counted)"
+                            if wl["extend"] else ""))
         else:
             per = (21 if wl["extend"] else 10) * n + 4
             alg = per * steps_mine
             formula = f"DenseOTF: {21 if wl['extend'] else 10} N + 4 per step"
+        del mine
         achieved = alg / kernel_s / 1e9
-        traffic = None
+        traffic, note = None, None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(args.workload, {}).get("dram_bytes_per_launch")
+            rec = json.load(open(tpath)).get(name, {})
+            if rec.get("kernel", kname) == kname:
+                traffic = rec.get("dram_bytes_per_launch")
+                note = rec.get("note")
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": traffic, "kernel": eng.kernel_name(wl["mode"], wl["p"], wl["q"], wl["extend"], args.flags), "kernel_ms": 1e3 * kernel_s,
+                    "traffic": traffic, "kernel": kname, "kernel_ms": 1e3 * kernel_s,
                     "algorithmic_bytes_per_launch": alg, "bytes_per_step": alg / max(steps_mine, 1),
                     "formula": formula, "peak_source": peak_src}
+        if traffic and world == 1:
+            # the kernel's REAL DRAM traffic on the same scale: what the HBM system actually delivers
+            roofline["dram_gbs"] = traffic / kernel_s / 1e9
+            roofline["dram_frac"] = traffic / kernel_s / 1e9 / peak
+            roofline["dram_bytes_per_step"] = traffic / max(steps_mine, 1)
+        if kname in ("walk_uw_edge_kernel", "walk_uw_kernel"):
+            roofline["note"] = ("`frac` is the contract's EFFECTIVE bandwidth: SURVEY 8d's row-streaming bytes / time. "
+                                "This kernel never streams rows (per-edge index: one 16-byte record per step), so frac "
+                                "can exceed 1; its own ceiling is the random-sector DRAM rate, see dram_frac")
+        elif note:
+            roofline["note"] = note
 
-    # ---------------- e2e through the host-buffer C-ABI entry point
+    # ---------------- e2e through the host-buffer C-ABI entry points: ONE host matrix
     e2e = None
-    if not args.no_e2e and my_rows >= 0:
-        h_start = torch.from_numpy(start[lo:hi].view(np.int32).copy()).pin_memory()
-        h_out = torch.empty((max(my_rows, 1), ld), dtype=torch.int32).pin_memory()
-        np_start = h_start.numpy().view(np.uint32)
-        np_out = h_out.numpy().view(np.uint32)[:my_rows]
-        del full, mine
-        torch.cuda.empty_cache()
-        reps = max(2, min(K, 3))
-        if my_rows:
-            eng.walk_host(wl["mode"], wl["p"], wl["q"], np_start, L, seed=7, extend=wl["extend"], row0=lo, out=np_out,
-                          flags=args.flags)
-        torch.cuda.synchronize(); barrier()
-        t0 = time.perf_counter()
-        for r in range(reps):
-            if my_rows:
-                eng.walk_host(wl["mode"], wl["p"], wl["q"], np_start, L, seed=r, extend=wl["extend"], row0=lo,
-                              out=np_out, flags=args.flags)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        td = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(td, op=dist.ReduceOp.MAX)
-        e2e = {"value": steps_job * reps / float(td[0]), "unit": "steps/s",
-               "h2d_bytes_per_step": int(4 * tot), "d2h_bytes_per_step": int(4 * ld * tot), "reps": reps,
-               "api": "WalkEngine.walk_host -> b2w_walk_host (pinned host start[] in, pinned host walk matrix out)"}
+    del full
+    torch.cuda.empty_cache()
+    if do_e2e:
+        e2e = run_e2e(torch, dist, eng, g, wl, start, L, K, rank, world, local_rank, steps_job, args)
 
     # ---------------- CPU baseline (rank 0, N=1 only)
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        prep_reference_extras(wl, g, eng)
-        rate, cores, sample, _ = cpu_port_rate(wl, g, start, L, 15.0, seed=0)
+    if rank == 0 and world == 1 and do_cpu:
+        if wl["extend"] and eng.thr is not None:
+            # input of the CPU port: the thresholds (bit-identical to the reference's NumPy loop, tests/) from the
+            # device instead of 13 us per node of Python
+            g["thr"] = eng.thr.cpu().numpy()
+        prep_reference_extras(wl, g)
+        rate, cores, sample, _ = cpu_port_rate(wl, g, start, L, cpu_budget, seed=0)
         cpu = {"value": rate, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}
 
+    line = None
     if rank == 0:
+        launches = K_eff * sum(1 for _, r in blocks if r)
         line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": 1e3 * t_total / max(K, 1), "higher_is_better": True, "scaling": "strong",
+                "ms_per_step": 1e3 * t_total / max(K_eff, 1), "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": dtype_of(wl), "data": "synthetic",
-                "config": config_of(args, wl, g, world), "clocks": clocks, "gpu_launches": K * (1 if my_rows else 0),
-                "steps_per_pass": steps_job, "kernel_ms_max_over_ranks": 1e3 * t_kernel_max / max(K, 1),
+                "config": config_of(args, name, wl, g, world, NB), "clocks": clocks, "gpu_launches": launches,
+                "timed_passes": K_eff, "steps_per_pass": steps_job,
+                "kernel_ms_max_over_ranks": 1e3 * t_kernel_max / max(K_eff, 1),
+                "checksum": {"seed": CHECK_SEED, "fnv_like_u64": checksum},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "walk_stats_rank0": walk_stats}
         line.update(extras)
+    eng.close()
+    del eng, d_start_all, flush
+    torch.cuda.empty_cache()
+    return line
+
+
+def run_e2e(torch, dist, eng, g, wl, start, L, K, rank, world, local_rank, steps_job, args):
+    """The call a user makes, host buffers in and out: b2w_walk_host on one GPU; with N > 1, b2w_walk_multi from
+    rank 0's process over all N GPUs of the box (one host thread per GPU, one pinned host matrix) while the other
+    ranks wait -- the single-process multi-GPU path of the drop-in classes (pecanpy_b200/multi.py)."""
+    from pecanpy_b200.engine import WalkEngine
+    tot, ld = start.size, L + 2
+    reps = max(2, min(K, 3))
+    dt = None
+    api = "WalkEngine.walk_host -> b2w_walk_host (pinned host start[] in, pinned host walk matrix out)"
+    if rank == 0:
+        h_start = torch.from_numpy(start.view(np.int32).copy()).pin_memory()
+        h_out = torch.empty((tot, ld), dtype=torch.int32).pin_memory()
+        np_start = h_start.numpy().view(np.uint32)
+        np_out = h_out.numpy().view(np.uint32)
+        if world == 1:
+            def call(seed):
+                eng.walk_host(wl["mode"], wl["p"], wl["q"], np_start, L, seed=seed, extend=wl["extend"], out=np_out,
+                              flags=args.flags)
+        else:
+            from pecanpy_b200.multi import walk_host_engines
+            engines = [eng]
+            for d in range(world):
+                if d == local_rank:
+                    continue
+                dv = torch.device("cuda", d)
+                e2 = (WalkEngine.from_dense(g["data"], g["nonzero"], device=dv) if g["kind"] == "dense"
+                      else WalkEngine.from_csr(g["indptr"], g["indices"], g["data"], device=dv))
+                if wl["extend"]:
+                    e2.compute_thresholds(wl.get("gamma", 0.0))
+                if wl["mode"] == "PreComp":
+                    e2.build_alias(g["indptr"], wl["p"], wl["q"], extend=wl["extend"])
+                engines.append(e2)
+            api = (f"walk_host_engines -> b2w_walk_multi: one process, {world} GPUs, one host thread per GPU, pinned host "
+                   "start[] in, ONE pinned host walk matrix out")
+
+            def call(seed):
+                walk_host_engines(engines, wl["mode"], wl["p"], wl["q"], wl["extend"], np_start, L, seed, out=np_out,
+                                  flags=args.flags)
+        t0 = time.perf_counter()
+        call(7)                                             # warm-up: staging buffers, edge index of the replicas
+        if time.perf_counter() - t0 < 0.5:
+            call(8)
+        else:
+            reps = 2                                        # long passes: keep the default run within minutes
+        for d in range(world if world > 1 else 1):
+            torch.cuda.synchronize(d if world > 1 else local_rank)
+        t0 = time.perf_counter()
+        for r in range(reps):
+            call(r)
+        dt = time.perf_counter() - t0
+        if world > 1:
+            for e2 in engines[1:]:
+                e2.close()
+        del h_out, h_start
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        return None
+    return {"value": steps_job * reps / dt, "unit": "steps/s", "h2d_bytes_per_step": int(4 * tot),
+            "d2h_bytes_per_step": int(4 * ld * tot), "reps": reps, "api": api}
+
+
+# ------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (debug only; invalidates the number)")
+    ap.add_argument("--num-walks", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the sub-benchmarks of the other BASELINE configs")
+    ap.add_argument("--batches", type=int, default=8, help="N > 1: all-gather batches overlapped with the walk")
+    ap.add_argument("--flags", type=int, default=0, help="b2w_walk flags (debug)")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    K, W = max(args.steps, 1), max(args.warmup, 0)
+
+    # ---------------- reference arm: CPU port on rank 0 only
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        wl = dict(WORKLOADS[args.workload])
+        if args.num_walks:
+            wl["num_walks"] = args.num_walks
+        L = wl["L"]
+        g = make_graph(wl, args.scale, 0, lambda: None)
+        prep_reference_extras(wl, g)
+        from pecanpy_b200 import synth
+        start = synth.shuffled_start(g["n"], wl["num_walks"], 0)
+        per_step_budget = max(2.0, 150.0 / max(K + W, 1))
+        rate0, cores, _, rows = cpu_port_rate(wl, g, start, L, per_step_budget, seed=0)
+        times, steps = [], 0
+        for it in range(W + K):
+            t0 = time.perf_counter()
+            out = cpu_walk(wl, g, start[:rows], L, it, cores)
+            dt = time.perf_counter() - t0
+            if it >= W:
+                times.append(dt)
+                steps += int((out[:, -1].astype(np.int64) - 1).sum())
+        value = steps / sum(times)
+        sample = f"each step = first {rows} rows of the shuffled start array x {L} steps"
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": args.gpus,
+                "steps": K, "warmup": W, "ms_per_step": 1e3 * sum(times) / max(K, 1), "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": dtype_of(wl), "data": "synthetic",
+                "config": config_of(args, args.workload, wl, g, 1, 1),
+                "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ---------------- our arm
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    line = run_workload(args.workload, args, K, W, rank, world, local_rank, do_e2e=not args.no_e2e,
+                        do_cpu=not args.no_cpu)
+    if world == 1 and args.workload == DEFAULT_WORKLOAD and not args.no_extra and not args.num_walks \
+            and args.scale == 1.0 and not args.flags:
+        extra = {}
+        for name, w_, k_ in EXTRA:
+            t0 = time.time()
+            try:
+                sub = run_workload(name, args, k_, w_, rank, world, local_rank, do_e2e=not args.no_e2e,
+                                   do_cpu=not args.no_cpu, cpu_budget=4.0, min_timed_s=MIN_TIMED_S)
+                sub["steps"] = sub["timed_passes"]
+                for key in ("higher_is_better", "scaling", "vs_baseline", "data", "n_gpus", "metric", "unit"):
+                    sub.pop(key, None)
+                sub["bench_wall_s"] = round(time.time() - t0, 1)
+                extra[name] = sub
+            except Exception as exc:                          # a sub-benchmark must not take the headline down
+                extra[name] = {"error": repr(exc)}
+            log(f"[bench] extra {name}: {time.time() - t0:.1f}s")
+        line["extra"] = extra
+    if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -475,16 +652,18 @@ def dtype_of(wl):
     return "f64" if wl["mode"] == "DenseOTF" else "f32"
 
 
-def config_of(args, wl, g, world):
-    return {"workload": args.workload, "mode": wl["mode"], "p": wl["p"], "q": wl["q"], "extend": wl["extend"],
+def config_of(args, name, wl, g, world, nb):
+    return {"workload": name, "baseline_config": wl.get("config"), "mode": wl["mode"], "p": wl["p"], "q": wl["q"],
+            "extend": wl["extend"], "weighted": wl["weighted"],
             "num_nodes": g["n"], "nnz": int(g["indptr"][-1]) if g["kind"] == "csr" else None,
             "num_walks": wl["num_walks"], "walk_length": wl["L"], "rng": "philox4x32-10 keyed by (seed, global row, step)",
-            "parallelism": f"graph replicated, walkers sharded over {world} GPU(s), one NCCL all-gather" if world > 1
-            else "1 GPU", "l2": "256 MiB buffer written between timed iterations (L2 flush); graph+walk matrix exceed L2",
+            "parallelism": (f"graph replicated, walkers sharded over {world} GPU(s), {nb} all-gather batch(es) over NCCL "
+                            "overlapped with the walk of the next batch") if world > 1 else "1 GPU",
+            "l2": "256 MiB buffer written between timed iterations (L2 flush); graph+walk matrix exceed L2",
             "scale": args.scale}
 
 
-def prep_reference_extras(wl, g, eng=None):
+def prep_reference_extras(wl, g):
     """Host-side inputs the CPU arm needs: node2vec+ thresholds, PreComp tables (built by the port itself)."""
     from oracle import oracle as orc
     if wl["extend"] and "thr" not in g:

@@ -244,11 +244,26 @@ const char* b2w_walk_kernel_name(const b2w_graph* g, int mode, double p, double 
 /* Host-buffer convenience wrapper (the end-to-end call): copies h_start to the device in
  * batches, walks, and copies the rows back into h_out [n_rows, walk_length + 2]; H2D, kernel and
  * D2H of consecutive batches overlap on internal streams.  Pinned host buffers are used
- * directly; pageable buffers work but copy slower.  Synchronous.  h_stats may be NULL. */
+ * directly; pageable buffers work but copy slower.  Synchronous.  h_stats may be NULL.
+ * Stream contract: the internal streams are ordered after the work already queued on the device's DEFAULT stream
+ * (e.g. b2w_alias_build / b2w_noise_thresholds with stream = NULL); inputs produced on any OTHER stream must be
+ * complete before the call (synchronise that stream). */
 int b2w_walk_host(const b2w_graph* g, int mode, double p, double q, int extend, const float* d_thr,
                   const uint32_t* h_start, uint64_t row0, uint64_t n_rows, uint32_t walk_length,
                   uint64_t seed, uint32_t* h_out, uint64_t batch_rows, b2w_walk_stats* h_stats,
                   uint32_t flags);
+
+/* The same job on SEVERAL GPUs from one process (walkers are independent, the graph is read-only):
+ * graphs[k] is a replica of the graph on its own device (thresholds / alias tables / edge index attached per
+ * replica; d_thr[k] lives on that device, d_thr may be NULL without node2vec+).  Replica k walks the contiguous block
+ * [k R, (k + 1) R), R = ceil(n_rows / n_graphs), of the start array on its own host thread and delivers its rows
+ * straight into its slice of the ONE host matrix h_out [n_rows, walk_length + 2] -- the call a single-process host
+ * (e.g. PecanPy's simulate_walks) makes to use every GPU of the box.  Philox is keyed by the global row: the matrix
+ * is bit-identical for any number of replicas.  Synchronous.  (Multi-process jobs -- one rank per GPU -- call
+ * b2w_walk with row0 and all-gather the device blocks with NCCL: pecanpy_b200/dist.py.) */
+int b2w_walk_multi(int n_graphs, b2w_graph* const* graphs, int mode, double p, double q, int extend,
+                   const float* const* d_thr, const uint32_t* h_start, uint64_t n_rows, uint32_t walk_length,
+                   uint64_t seed, uint32_t* h_out, uint64_t batch_rows, b2w_walk_stats* h_stats, uint32_t flags);
 
 /* Sum of (effective_length - 1) over the rows of a device walk matrix (the metric's unit). */
 int b2w_count_steps(const uint32_t* d_out, uint64_t n_rows, uint32_t walk_length, uint64_t ld_out,

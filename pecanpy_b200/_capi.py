@@ -37,6 +37,7 @@ EXPORTS = [
     "b2w_alias_build_first_order", "b2w_graph_set_alias", "b2w_walk_work_bytes", "b2w_walk", "b2w_walk_host",
     "b2w_count_steps", "b2w_philox_selftest", "b2w_walk_kernel_name", "b2w_noise_thresholds", "b2w_csr_from_edges_work_bytes", "b2w_csr_from_edges",
     "b2w_edgelist_parse", "b2w_edgelist_fetch", "b2w_edgelist_free",
+    "b2w_walk_multi", "b2w_alias_build_packed", "b2w_graph_set_alias_packed",
     "b2w_edge_index_work_bytes", "b2w_edge_index_prepare", "b2w_edge_index_finish", "b2w_graph_set_edge_index",
 ]
 
@@ -81,10 +82,14 @@ def lib():
     L.b2w_alias_build.argtypes = [vp, dbl, dbl, i32, vp, vp, vp, vp, vp, sz, vp]
     L.b2w_alias_build_first_order.argtypes = [vp, vp, vp, vp, sz, vp]
     L.b2w_graph_set_alias.argtypes = [vp, vp, vp, vp]
+    L.b2w_alias_build_packed.argtypes = [vp, dbl, dbl, i32, vp, vp, vp, vp, sz, vp]
+    L.b2w_graph_set_alias_packed.argtypes = [vp, vp, vp]
     L.b2w_walk_work_bytes.argtypes = [vp, i32]
     L.b2w_walk_work_bytes.restype = sz
     L.b2w_walk.argtypes = [vp, i32, dbl, dbl, i32, vp, vp, u64, u64, u32, u64, i32, vp, vp, u64, vp, sz, vp, u32, vp]
     L.b2w_walk_host.argtypes = [vp, i32, dbl, dbl, i32, vp, vp, u64, u64, u32, u64, vp, u64, C.POINTER(WalkStats), u32]
+    L.b2w_walk_multi.argtypes = [i32, C.POINTER(vp), i32, dbl, dbl, i32, C.POINTER(vp), vp, u64, u32, u64, vp, u64,
+                                 C.POINTER(WalkStats), u32]
     L.b2w_walk_kernel_name.argtypes = [vp, i32, dbl, dbl, i32, u32]
     L.b2w_walk_kernel_name.restype = C.c_char_p
     L.b2w_noise_thresholds.argtypes = [vp, dbl, vp, vp]

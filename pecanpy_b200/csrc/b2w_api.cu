@@ -6,6 +6,9 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "b2w_common.cuh"
 
@@ -89,8 +92,10 @@ struct b2w_host_pipe {
   uint32_t* d_out[NS] = {nullptr, nullptr};
   void* d_work[NS] = {nullptr, nullptr};
   b2w_walk_stats* d_stats = nullptr;
+  cudaEvent_t ev = nullptr;
   size_t start_cap = 0, out_cap = 0, work_cap = 0;
   void release() {
+    if (ev) { cudaEventDestroy(ev); ev = nullptr; }
     for (int k = 0; k < NS; ++k) {
       if (d_start[k]) cudaFree(d_start[k]);
       if (d_out[k]) cudaFree(d_out[k]);
@@ -390,6 +395,14 @@ extern "C" int b2w_walk_host(const b2w_graph* g, int mode, double p, double q, i
   cudaError_t e = pipe->ensure(batch_rows * sizeof(uint32_t), batch_rows * ld * sizeof(uint32_t), wb);
   if (e == cudaSuccess) e = cudaMemsetAsync(pipe->d_stats, 0, sizeof(b2w_walk_stats), pipe->st[0]);
   if (e == cudaSuccess) e = cudaStreamSynchronize(pipe->st[0]);
+  // The internal streams are non-blocking: order them after whatever the caller queued on the default stream of
+  // this device (tables / thresholds built just before, e.g. by b2w_alias_build(..., stream = NULL)).  Producers on
+  // OTHER streams must be synchronised by the caller (b2w.h).
+  if (e == cudaSuccess) {
+    if (!pipe->ev) e = cudaEventCreateWithFlags(&pipe->ev, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(pipe->ev, cudaStreamLegacy);
+    for (int k = 0; k < b2w_host_pipe::NS && e == cudaSuccess; ++k) e = cudaStreamWaitEvent(pipe->st[k], pipe->ev, 0);
+  }
   if (e != cudaSuccess) { pipe->release(); return b2w_cuda_fail(e, "b2w_walk_host setup"); }
   uint64_t done = 0;
   for (int b = 0; rc == B2W_OK && done < n_rows; ++b) {
@@ -414,6 +427,57 @@ extern "C" int b2w_walk_host(const b2w_graph* g, int mode, double p, double q, i
     if (e != cudaSuccess) rc = b2w_cuda_fail(e, "stats D2H");
   }
   return rc;
+}
+
+// ---------------------------------------------------------------- several GPUs from one process
+// Walkers never interact (pecanpy.py:189-206 writes only row i) and the graph is read-only, so rows shard freely:
+// replica k of the graph (one handle per device) walks the contiguous block [k R, (k + 1) R) of the start array,
+// R = ceil(n_rows / n_graphs), on its own host thread through b2w_walk_host, straight into its slice of the ONE host
+// matrix.  Philox is keyed by the global row, so the matrix is identical for any number of devices.
+extern "C" int b2w_walk_multi(int n_graphs, b2w_graph* const* graphs, int mode, double p, double q, int extend,
+                              const float* const* d_thr, const uint32_t* h_start, uint64_t n_rows, uint32_t L,
+                              uint64_t seed, uint32_t* h_out, uint64_t batch_rows, b2w_walk_stats* h_stats,
+                              uint32_t flags) {
+  if (n_graphs < 1 || !graphs) { b2w_set_error("b2w_walk_multi: no graph replicas"); return B2W_ERR_INVALID; }
+  for (int k = 0; k < n_graphs; ++k) {
+    if (!graphs[k]) { b2w_set_error("b2w_walk_multi: null replica %d", k); return B2W_ERR_INVALID; }
+    for (int j = 0; j < k; ++j)
+      if (graphs[j] == graphs[k]) { b2w_set_error("b2w_walk_multi: replica %d listed twice (one handle per device)", k); return B2W_ERR_INVALID; }
+  }
+  if (n_rows == 0) return B2W_OK;
+  if (!h_start || !h_out) { b2w_set_error("b2w_walk_multi: null start/out"); return B2W_ERR_INVALID; }
+  const uint64_t R = (n_rows + (uint64_t)n_graphs - 1) / (uint64_t)n_graphs;
+  const uint64_t ld = (uint64_t)L + 2;
+  std::vector<int> rc((size_t)n_graphs, B2W_OK);
+  std::vector<std::string> msg((size_t)n_graphs);
+  std::vector<b2w_walk_stats> st((size_t)n_graphs);
+  std::vector<std::thread> th;
+  try {
+    for (int k = 0; k < n_graphs; ++k) {
+      const uint64_t lo = (uint64_t)k * R < n_rows ? (uint64_t)k * R : n_rows;
+      const uint64_t hi = lo + R < n_rows ? lo + R : n_rows;
+      th.emplace_back([&, k, lo, hi]() {
+        memset(&st[(size_t)k], 0, sizeof(b2w_walk_stats));
+        if (hi <= lo) return;
+        rc[(size_t)k] = b2w_walk_host(graphs[k], mode, p, q, extend, d_thr ? d_thr[k] : nullptr, h_start + lo, lo, hi - lo, L,
+                                      seed, h_out + lo * ld, batch_rows, &st[(size_t)k], flags);
+        if (rc[(size_t)k]) msg[(size_t)k] = b2w_last_error();       // the message is thread-local: carry it over
+      });
+    }
+  } catch (...) {
+    for (auto& t : th) t.join();
+    b2w_set_error("b2w_walk_multi: cannot start a host thread per device");
+    return B2W_ERR_NOMEM;
+  }
+  for (auto& t : th) t.join();
+  b2w_walk_stats tot{};
+  for (int k = 0; k < n_graphs; ++k) {
+    if (rc[(size_t)k]) { b2w_set_error("b2w_walk_multi: replica %d: %s", k, msg[(size_t)k].c_str()); return rc[(size_t)k]; }
+    tot.steps += st[(size_t)k].steps; tot.exact_replays += st[(size_t)k].exact_replays;
+    tot.seq_sums += st[(size_t)k].seq_sums; tot.overflow_choices += st[(size_t)k].overflow_choices;
+  }
+  if (h_stats) *h_stats = tot;
+  return B2W_OK;
 }
 
 // ---------------------------------------------------------------- helpers

@@ -135,6 +135,7 @@ class WalkEngine:
             stream = torch.cuda.current_stream(self.device).cuda_stream
             capi.check(self.lib.b2w_noise_thresholds(self.handle, float(gamma), _ptr(thr), C.c_void_p(stream)),
                        "b2w_noise_thresholds")
+            torch.cuda.current_stream(self.device).synchronize()   # consumers may run on other streams (b2w_walk_host)
         self.thr = thr
         return thr
 
@@ -219,35 +220,57 @@ class WalkEngine:
         out[1:] = np.cumsum(deg * deg)
         return out
 
-    def build_alias(self, indptr: np.ndarray, p: float, q: float, extend: bool = False, first_order: bool = False):
-        """Build the alias tables on the GPU and attach them to the handle."""
+    def build_alias(self, indptr: np.ndarray, p: float, q: float, extend: bool = False, first_order: bool = False,
+                    packed: Optional[bool] = None):
+        """Build the alias tables on the GPU and attach them to the handle.
+
+        ``packed`` (default for PreComp): ONE table of 8-byte ``{q, j}`` entries (b2w_alias_build_packed) so that a
+        draw touches one memory sector; ``self.alias`` still presents the reference's two arrays -- as strided views
+        of the packed table, bit-identical to ``alias_j`` / ``alias_q`` of pecanpy.py:442-507.  The call returns
+        after the build kernel has finished (the walk entry points may run on other streams)."""
         if self.kind != "csr":
             raise ValueError("alias tables need a CSR graph")
+        if packed is None:
+            packed = not first_order
         gi = self.info()
         with torch.cuda.device(self.device):
-            stream = torch.cuda.current_stream(self.device).cuda_stream
+            stream = torch.cuda.current_stream(self.device)
             wb = int(self.lib.b2w_alias_build_work_bytes(self.handle))
             work = self._scratch("alias", wb)
+            aqj = None
             if first_order:
                 tot = int(indptr[-1])
                 aj = torch.zeros(tot + gi.max_degree + 1, dtype=torch.int32, device=self.device)
                 aq = torch.zeros(tot + gi.max_degree + 1, dtype=torch.float32, device=self.device)
                 capi.check(self.lib.b2w_alias_build_first_order(self.handle, _ptr(aj), _ptr(aq), _ptr(work), wb,
-                                                                C.c_void_p(stream)), "b2w_alias_build_first_order")
+                                                                C.c_void_p(stream.cuda_stream)), "b2w_alias_build_first_order")
                 aip_h, aip_d = None, None
             else:
                 aip_h = self.alias_indptr(np.ascontiguousarray(indptr, dtype=np.uint32))
                 tot = int(aip_h[-1])
                 aip_d = _to_dev(aip_h, self.device, np.int64)
-                aj = torch.zeros(tot + gi.max_degree + 1, dtype=torch.int32, device=self.device)
-                aq = torch.zeros(tot + gi.max_degree + 1, dtype=torch.float32, device=self.device)
                 if extend and self.thr is None:
                     raise ValueError("extend=True needs set_thresholds() first")
-                capi.check(self.lib.b2w_alias_build(self.handle, float(p), float(q), int(bool(extend)),
-                                                    _ptr(self.thr if extend else None), _ptr(aip_d), _ptr(aj), _ptr(aq),
-                                                    _ptr(work), wb, C.c_void_p(stream)), "b2w_alias_build")
-            capi.check(self.lib.b2w_graph_set_alias(self.handle, _ptr(aip_d), _ptr(aj), _ptr(aq)), "b2w_graph_set_alias")
-        self._keep["alias_indptr"], self._keep["alias_j"], self._keep["alias_q"] = aip_d, aj, aq
+                thr = _ptr(self.thr if extend else None)
+                if packed:
+                    aqj = torch.zeros(tot + gi.max_degree + 1, dtype=torch.int64, device=self.device)
+                    capi.check(self.lib.b2w_alias_build_packed(self.handle, float(p), float(q), int(bool(extend)), thr,
+                                                               _ptr(aip_d), _ptr(aqj), _ptr(work), wb,
+                                                               C.c_void_p(stream.cuda_stream)), "b2w_alias_build_packed")
+                    pair = aqj.view(torch.int32).view(-1, 2)          # [:, 0] = q bits, [:, 1] = j
+                    aq, aj = pair[:, 0].view(torch.float32), pair[:, 1]
+                else:
+                    aj = torch.zeros(tot + gi.max_degree + 1, dtype=torch.int32, device=self.device)
+                    aq = torch.zeros(tot + gi.max_degree + 1, dtype=torch.float32, device=self.device)
+                    capi.check(self.lib.b2w_alias_build(self.handle, float(p), float(q), int(bool(extend)), thr,
+                                                        _ptr(aip_d), _ptr(aj), _ptr(aq), _ptr(work), wb,
+                                                        C.c_void_p(stream.cuda_stream)), "b2w_alias_build")
+            if aqj is not None:
+                capi.check(self.lib.b2w_graph_set_alias_packed(self.handle, _ptr(aip_d), _ptr(aqj)), "b2w_graph_set_alias_packed")
+            else:
+                capi.check(self.lib.b2w_graph_set_alias(self.handle, _ptr(aip_d), _ptr(aj), _ptr(aq)), "b2w_graph_set_alias")
+            stream.synchronize()          # b2w_walk_host runs on its own streams: the tables must be complete
+        self._keep["alias_indptr"], self._keep["alias_j"], self._keep["alias_q"], self._keep["alias_qj"] = aip_d, aj, aq, aqj
         self.alias = (aip_h, aj[:tot], aq[:tot])
         return self.alias
 

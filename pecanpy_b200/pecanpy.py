@@ -40,18 +40,35 @@ class Base(BaseGraph):
         self.gamma = gamma
         self.random_state = random_state
         self._preprocessed = False
+        self._preprocess_key = None
         self._engine = None
+        self._engine_key = None
+        self._replicas = {}
+        self._alias_dev = None
         self.device = None          # torch device string/obj; None = current CUDA device
+        self.devices = None         # list of CUDA devices for single-process multi-GPU walks (None = one GPU)
         self.last_seed = None
 
     # -- engine ------------------------------------------------------------------------------
     def _make_engine(self):
         raise NotImplementedError
 
+    def _graph_key(self):
+        """Identity of what the device copy was made from.  The reference rebuilds its closures from the current
+        arrays on every simulate_walks call (pecanpy.py:143-144); here the device copy is cached and must be dropped
+        when the graph is reloaded (read_edg / read_npz / from_mat), an array is re-assigned, or gamma changes."""
+        raise NotImplementedError
+
+    def _engine_stale(self) -> bool:
+        return self._engine is not None and self._engine_key != (self._graph_key(), self.extend, self.gamma)
+
     @property
     def engine(self):
+        if self._engine_stale():
+            self.release()
         if self._engine is None:
             self._engine = self._make_engine()
+            self._engine_key = (self._graph_key(), self.extend, self.gamma)
             if self.extend and self._MODE in ("SparseOTF", "DenseOTF", "PreComp"):
                 self._engine.compute_thresholds(self.gamma)
         return self._engine
@@ -64,23 +81,35 @@ class Base(BaseGraph):
         return thr.cpu().numpy()
 
     def release(self):
+        """Drop the device copy of the graph (and everything derived from it: thresholds, alias tables, edge index)."""
         if self._engine is not None:
             self._engine.close()
-            self._engine = None
-            self._preprocessed = False
+        for e in getattr(self, "_replicas", {}).values():
+            e.close()
+        self._replicas = {}
+        self._engine = None
+        self._engine_key = None
+        self._preprocessed = False
+        self._preprocess_key = None
+        self._alias_dev = None
+        if hasattr(self, "_alias_host"):
+            self._alias_host = None
 
     # -- reference surface ---------------------------------------------------------------------
     def preprocess_transition_probs(self):
         """Null default (pecanpy.py:231-233)."""
 
     def _preprocess_transition_probs(self):
-        if not self._preprocessed:
+        key = (self._graph_key(), self.extend, self.gamma, float(self.p), float(self.q))
+        if self._engine_stale() or not self._preprocessed or self._preprocess_key != key:
+            _ = self.engine                      # (re)creates the device copy if the graph changed
             self.preprocess_transition_probs()
             self._preprocessed = True
+            self._preprocess_key = key
 
     def _start_nodes(self, num_walks: int) -> np.ndarray:
         # pecanpy.py:135-141, verbatim semantics: NumPy legacy global generator
-        nodes = np.array(range(self.num_nodes), dtype=np.uint32)
+        nodes = np.arange(self.num_nodes, dtype=np.uint32)            # == np.array(range(n), dtype=np.uint32)
         start = np.concatenate([nodes] * num_walks)
         np.random.seed(self.random_state)
         np.random.shuffle(start)
@@ -92,11 +121,17 @@ class Base(BaseGraph):
         return self.last_seed
 
     def simulate_walks_array(self, num_walks: int, walk_length: int) -> np.ndarray:
-        """Raw walk matrix ``uint32[num_nodes * num_walks, walk_length + 2]`` (host)."""
+        """Raw walk matrix ``uint32[num_nodes * num_walks, walk_length + 2]`` (host), layout of pecanpy.py:182-206.
+        With ``self.devices`` set to several CUDA devices the rows are sharded over them from THIS process (one
+        host thread per GPU, graph replicated, Philox keyed by the global row: the matrix is identical for any
+        number of GPUs) -- simulate_walks stays a plain call, no torchrun."""
         self._preprocess_transition_probs()
         start = self._start_nodes(num_walks)
-        return self.engine.walk_host(self._MODE, self.p, self.q, start, walk_length, self._seed(),
-                                     extend=bool(self.extend))
+        seed = self._seed()
+        if self.devices and len(self.devices) > 1:
+            from .multi import walk_host_multi
+            return walk_host_multi(self, start, walk_length, seed)
+        return self.engine.walk_host(self._MODE, self.p, self.q, start, walk_length, seed, extend=bool(self.extend))
 
     def _map_walk(self, walk_idx_ary) -> List[str]:
         end_idx = walk_idx_ary[-1]
@@ -134,9 +169,12 @@ class _SparseBase(Base, SparseGraph):
         self.indptr = None
         self.indices = None
 
-    def _make_engine(self):
+    def _graph_key(self):
+        return tuple((id(a), getattr(a, "shape", None)) for a in (self.indptr, self.indices, self.data))
+
+    def _make_engine(self, device=None):
         from .engine import WalkEngine
-        return WalkEngine.from_csr(self.indptr, self.indices, self.data, device=self.device)
+        return WalkEngine.from_csr(self.indptr, self.indices, self.data, device=device or self.device)
 
 
 class SparseOTF(_SparseBase):
@@ -149,16 +187,42 @@ class FirstOrderUnweighted(_SparseBase):
     _MODE = "FirstOrderUnweighted"
 
 
-class PreComp(_SparseBase):
+class _AliasTables:
+    """alias_j / alias_q as in the reference (populated attributes after preprocess_transition_probs,
+    pecanpy.py:505-507): copied from the device on first access."""
+
+    def _fetch_alias(self):
+        if self._alias_host is None:
+            if self._alias_dev is None:
+                return None
+            aj, aq = self._alias_dev
+            self._alias_host = (aj.cpu().numpy().view(np.uint32).copy(), aq.cpu().numpy().copy())
+        return self._alias_host
+
+    @property
+    def alias_j(self):
+        t = self._fetch_alias()
+        return None if t is None else t[0]
+
+    @property
+    def alias_q(self):
+        t = self._fetch_alias()
+        return None if t is None else t[1]
+
+    def fetch_alias_tables(self):
+        """(alias_j uint32, alias_q float32) on the host -- same arrays as the two properties."""
+        return self.alias_j, self.alias_q
+
+
+class PreComp(_AliasTables, _SparseBase):
     """Pre-computed 2nd-order alias tables (reference pecanpy.py:364-507); tables are built on the GPU."""
     _MODE = "PreComp"
 
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
         self.alias_dim = None
-        self.alias_j = None
-        self.alias_q = None
         self.alias_indptr = None
+        self._alias_host = None
 
     def preprocess_transition_probs(self):
         eng = self.engine
@@ -166,26 +230,21 @@ class PreComp(_SparseBase):
         self.alias_dim = (self.indptr[1:] - self.indptr[:-1]).astype(np.uint32)
         self.alias_indptr = aip
         self._alias_dev = (aj, aq)
-
-    def fetch_alias_tables(self):
-        """Copy the tables to the host as the reference's attributes (alias_j uint32, alias_q float32)."""
-        aj, aq = self._alias_dev
-        self.alias_j = aj.cpu().numpy().view(np.uint32)
-        self.alias_q = aq.cpu().numpy()
-        return self.alias_j, self.alias_q
+        self._alias_host = None
 
 
-class PreCompFirstOrder(_SparseBase):
+class PreCompFirstOrder(_AliasTables, _SparseBase):
     """Pre-computed first-order alias tables (reference pecanpy.py:312-361)."""
     _MODE = "PreCompFirstOrder"
 
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
-        self.alias_j = self.alias_q = None
+        self._alias_host = None
 
     def preprocess_transition_probs(self):
         _, aj, aq = self.engine.build_alias(self.indptr, 1.0, 1.0, first_order=True)
         self._alias_dev = (aj, aq)
+        self._alias_host = None
 
 
 class DenseOTF(Base, DenseGraph):
@@ -197,6 +256,9 @@ class DenseOTF(Base, DenseGraph):
         self._data = None
         self._nonzero = None
 
-    def _make_engine(self):
+    def _graph_key(self):
+        return ((id(self._data), getattr(self._data, "shape", None)),)
+
+    def _make_engine(self, device=None):
         from .engine import WalkEngine
-        return WalkEngine.from_dense(self.data, self.nonzero, device=self.device)
+        return WalkEngine.from_dense(self.data, self.nonzero, device=device or self.device)

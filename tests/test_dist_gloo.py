@@ -1,6 +1,7 @@
 """Host logic of the N>1 path on CPU: world_size 2, gloo.  The walk function injected here is the CPU
-oracle (test infrastructure) -- what is under test is the row sharding, the global-row RNG keying and
-the all-gather layout of pecanpy_b200/dist.py, which are device independent."""
+oracle (test infrastructure) -- what is under test is the row sharding into batches, the global-row RNG keying and
+the batch-wise all-gather layout of pecanpy_b200/dist.py, which are device independent.  The CUDA kernels on two
+ranks are covered by tests/test_gpu_multi.py."""
 import os
 import socket
 
@@ -19,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, total_rows, q):
+def _worker(rank, world, port, total_rows, batches, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -34,15 +35,15 @@ def _worker(rank, world, port, total_rows, q):
                          rng=orc.RNG_PHILOX, seed=11, row0=lo, nthreads=1)
         out_block[: hi - lo].copy_(torch.from_numpy(w.view(np.int32)))
 
-    full = sharded_walks(walk_block, total_rows, L + 2, "cpu")
-    lo, hi, R = shard_rows(total_rows, world, rank)
-    q.put((rank, lo, hi, R, full.numpy().view(np.uint32).copy()))
+    full = sharded_walks(walk_block, total_rows, L + 2, "cpu", batches=batches)
+    blocks, B = shard_rows(total_rows, world, rank, batches)
+    q.put((rank, blocks, B, full.numpy().view(np.uint32).copy()))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("total_rows", [800, 777])
-def test_sharded_walks_match_single_process(total_rows):
+@pytest.mark.parametrize("total_rows,batches", [(800, 1), (777, 1), (777, 3), (50, 4)])
+def test_sharded_walks_match_single_process(total_rows, batches):
     from oracle import oracle as orc
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hub400_sparseotf_n2v.npz"))
     want = orc.walk_csr("SparseOTF", z["indptr"], z["indices"], z["data"], 4, 0.25, z["start"][:total_rows], 12,
@@ -50,25 +51,38 @@ def test_sharded_walks_match_single_process(total_rows):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, total_rows, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, total_rows, batches, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    blocks = sorted(res)
-    assert blocks[0][1] == 0 and blocks[0][2] == blocks[1][1] and blocks[1][2] == total_rows
-    for _, _, _, _, full in blocks:           # every rank ends with the whole matrix
-        assert np.array_equal(full, want)
+    res = sorted(res, key=lambda t: t[0])
+    covered = np.zeros(total_rows, dtype=np.int32)
+    for _, blocks, B, full in res:
+        assert len(blocks) == batches
+        for lo, hi in blocks:
+            covered[lo:hi] += 1
+        assert np.array_equal(full, want)      # every rank ends with the whole matrix
+    assert (covered == 1).all()                # the ranks' blocks tile the rows exactly once
 
 
 def test_shard_rows_cover_everything():
     from pecanpy_b200.dist import shard_rows
     for tot in [0, 1, 7, 8, 9, 1000, 10_000_000]:
         for world in [1, 2, 3, 4, 8]:
-            spans = [shard_rows(tot, world, r) for r in range(world)]
-            assert spans[0][0] == 0 and spans[-1][1] == tot
-            for a, b in zip(spans, spans[1:]):
-                assert a[1] == b[0]
-            assert all(s[2] * world >= tot for s in spans)
+            for batches in [1, 2, 8]:
+                covered = 0
+                spans = []
+                for r in range(world):
+                    blocks, B = shard_rows(tot, world, r, batches)
+                    assert B * world * batches >= tot
+                    for b, (lo, hi) in enumerate(blocks):
+                        assert hi - lo <= B and (hi == lo or lo == (b * world + r) * B)
+                        spans.append((lo, hi))
+                        covered += hi - lo
+                assert covered == tot
+                spans = sorted(s for s in spans if s[1] > s[0])
+                for a, b2 in zip(spans, spans[1:]):
+                    assert a[1] == b2[0]

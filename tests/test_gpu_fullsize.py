@@ -85,3 +85,65 @@ def test_full_size_sparse_otf(workload):
     want = orc.walk_csr("SparseOTF", indptr, indices, data, p, q, start[:k], L, rng=orc.RNG_PHILOX, seed=5)
     assert np.array_equal(a[:k].cpu().numpy().view(np.uint32), want)
     eng.close()
+
+
+def test_full_size_precomp_config4():
+    """BASELINE config #4 at full size: ER 50k nodes / 1M edges, weighted, PreComp p=0.25 q=4 -- 8.2e7 table entries
+    (656 MB).  Tables byte-identical to the oracle's (packed layout, de-interleaved view), a 20k-row prefix of the
+    walks equals the oracle, and both walk kernels / both table layouts give the same matrix for all 5e5 rows."""
+    import torch
+    from oracle import oracle as orc
+    from pecanpy_b200 import synth
+    from pecanpy_b200.engine import WalkEngine
+    indptr, indices, data = synth.erdos_renyi_csr(50_000, 1_000_000, seed=2, weighted=True)
+    p, q, L = 0.25, 4.0, 80
+    start = synth.shuffled_start(50_000, 10, 0)
+    eng = WalkEngine.from_csr(indptr, indices, data, device="cuda:0")
+    aip, aj, aq = eng.build_alias(indptr, p, q)
+    o_aip, o_j, o_q = orc.alias_build(indptr, indices, data, p, q)
+    assert int(aip[-1]) > 80_000_000 and np.array_equal(aip, o_aip)
+    assert np.array_equal(aj.cpu().numpy().view(np.uint32), o_j)
+    assert np.array_equal(aq.cpu().numpy().view(np.uint32), o_q.view(np.uint32))
+    a = eng.walk("PreComp", p, q, start, L, seed=11)
+    assert eng.kernel_name("PreComp", p, q) == "walk_precomp_edge_kernel"
+    st = eng.stats()
+    b = eng.walk("PreComp", p, q, start, L, seed=11, flags=0x40)      # bisecting kernel, packed tables
+    assert torch.equal(a, b)
+    assert st["steps"] == eng.count_steps(a, L) == 50_000 * 10 * L
+    k = 20000
+    want = orc.walk_csr("PreComp", indptr, indices, data, p, q, start[:k], L, alias=(o_aip, o_j, o_q),
+                        rng=orc.RNG_PHILOX, seed=11)
+    assert np.array_equal(a[:k].cpu().numpy().view(np.uint32), want)
+    host = eng.walk_host("PreComp", p, q, start, L, seed=11)
+    assert np.array_equal(host, a.cpu().numpy().view(np.uint32))
+    eng2 = WalkEngine.from_csr(indptr, indices, data, device="cuda:0")
+    eng2.build_alias(indptr, p, q, packed=False)                      # the reference's two-array layout
+    c = eng2.walk("PreComp", p, q, start, L, seed=11, flags=0x40)
+    assert torch.equal(a, c)
+    eng.close(); eng2.close()
+
+
+def test_full_size_dense_config5():
+    """BASELINE config #5 at full size: dense 20 000 nodes, 30 % density, weighted, DenseOTF node2vec+ (gamma 0,
+    p=0.5 q=2): 20 TMA tiles per row with the 3-stage ring wrapping.  Thresholds equal the oracle's, a 2k-row prefix
+    of the walks equals the oracle, TMA and LDG load paths agree on every row."""
+    import torch
+    from oracle import oracle as orc
+    from pecanpy_b200 import synth
+    from pecanpy_b200.engine import WalkEngine
+    n, L = 20_000, 80
+    data, nz = synth.dense_weighted(n, 0.3, 3)
+    eng = WalkEngine.from_dense(data, nz, device="cuda:0")
+    thr = eng.compute_thresholds(0.0).cpu().numpy()
+    want_thr = orc.noise_thresholds_dense(data, nz, 0.0)
+    assert np.array_equal(thr.view(np.uint32), want_thr.view(np.uint32))
+    start = synth.shuffled_start(n, 2, 0)                            # 40 000 walkers
+    a = eng.walk("DenseOTF", 0.5, 2.0, start, L, seed=13, extend=True)             # TMA staged
+    st = eng.stats()
+    b = eng.walk("DenseOTF", 0.5, 2.0, start, L, seed=13, extend=True, flags=0x10)  # per-lane vector loads
+    assert torch.equal(a, b)
+    assert st["steps"] == eng.count_steps(a, L) == start.size * L
+    k = 1500
+    want = orc.walk_dense(data, nz, 0.5, 2.0, start[:k], L, extend=True, thr=want_thr, rng=orc.RNG_PHILOX, seed=13)
+    assert np.array_equal(a[:k].cpu().numpy().view(np.uint32), want)
+    eng.close()

@@ -137,10 +137,18 @@ def test_sparse_otf_philox_R2(mods, name, flags):
     eng.close()
 
 
+PRECOMP_VARIANTS = {"packed+edge-index": (True, 0), "packed": (True, 0x40), "two-arrays+edge-index": (False, 0),
+                    "two-arrays": (False, 0x40)}
+
+
+@pytest.mark.parametrize("variant", list(PRECOMP_VARIANTS), ids=list(PRECOMP_VARIANTS))
 @pytest.mark.parametrize("name", ["karate_precomp_p025_q4", "w200_precomp_n2v", "w200_precomp_ext",
                                   "dir150_precomp_deadends", "testwalk_PreComp"])
-def test_precomp_tables_and_walks(mods, name):
-    """Alias tables byte-identical to the reference's arrays (RNG-free parity), then Philox walks vs oracle."""
+def test_precomp_tables_and_walks(mods, name, variant):
+    """Alias tables byte-identical to the reference's arrays (RNG-free parity) in both table layouts (the
+    reference's two arrays / one packed {q, j} table), then Philox walks vs the oracle through both walk kernels
+    (per-edge records / bisection of prev in row(cur))."""
+    packed, flags = PRECOMP_VARIANTS[variant]
     c = load(name)
     orc = mods["orc"]
     L = int(c["walk_length"])
@@ -148,14 +156,17 @@ def test_precomp_tables_and_walks(mods, name):
     eng = mods["WalkEngine"].from_csr(c["indptr"], c["indices"], c["data"])
     if ext:
         eng.set_thresholds(c["thr"])
-    aip, aj, aq = eng.build_alias(c["indptr"], float(c["p"]), float(c["q"]), extend=ext)
+    aip, aj, aq = eng.build_alias(c["indptr"], float(c["p"]), float(c["q"]), extend=ext, packed=packed)
     assert np.array_equal(aip, c["alias_indptr"])
     assert np.array_equal(to_np(aj), c["alias_j"])
     assert np.array_equal(to_np(aq), c["alias_q"].view(np.uint32))
     want = orc.walk_csr("PreComp", c["indptr"], c["indices"], c["data"], float(c["p"]), float(c["q"]), c["start"], L,
                         alias=(c["alias_indptr"], c["alias_j"], c["alias_q"]), rng=orc.RNG_PHILOX, seed=99)
-    got = to_np(eng.walk("PreComp", float(c["p"]), float(c["q"]), c["start"], L, seed=99))
+    got = to_np(eng.walk("PreComp", float(c["p"]), float(c["q"]), c["start"], L, seed=99, flags=flags))
+    assert eng.kernel_name("PreComp", float(c["p"]), float(c["q"]), flags=flags) == \
+        ("walk_thread_kernel<PRECOMP>" if flags else "walk_precomp_edge_kernel")
     assert np.array_equal(got, want), first_diff(got, want)
+    assert eng.stats()["steps"] == int((want[:, -1].astype(np.int64) - 1).sum())
     eng.close()
 
 
@@ -176,6 +187,8 @@ def test_precomp_tables_hub_graph(mods, extend):
     want = orc.walk_csr("PreComp", c["indptr"], c["indices"], c["data"], 0.7, 0.3, c["start"], 20,
                         alias=(o_aip, o_j, o_q), rng=orc.RNG_PHILOX, seed=123)
     got = to_np(eng.walk("PreComp", 0.7, 0.3, c["start"], 20, seed=123))
+    assert np.array_equal(got, want), first_diff(got, want)
+    got = to_np(eng.walk("PreComp", 0.7, 0.3, c["start"], 20, seed=123, flags=0x40))   # without the edge records
     assert np.array_equal(got, want), first_diff(got, want)
     eng.close()
 
@@ -408,3 +421,65 @@ def test_dropin_extend_uses_device_thresholds(mods):
     want = mods["orc"].walk_csr("SparseOTF", c["indptr"], c["indices"], c["data"], float(c["p"]), float(c["q"]), start, 15,
                                 extend=True, thr=c["thr"], rng=mods["orc"].RNG_PHILOX, seed=11)
     assert np.array_equal(mat, want), first_diff(mat, want)
+
+
+def test_precomp_dropin_right_after_table_build(mods):
+    """Round-1 advice: preprocess (alias build, tens of ms) followed at once by the host-buffer walk on the
+    library's own streams -- the tables must be complete when the walk kernel reads them.  Also the lazily
+    copied alias_j / alias_q attributes of the reference surface."""
+    from pecanpy_b200 import pecanpy as b2
+    from pecanpy_b200.synth import erdos_renyi_csr
+    orc = mods["orc"]
+    indptr, indices, data = erdos_renyi_csr(20000, 600000, seed=8, weighted=True)
+    for extend in (False, True):
+        g = b2.PreComp(p=0.25, q=4, extend=extend, gamma=0.3, random_state=5)
+        g.indptr, g.indices, g.data = indptr, indices, data
+        g.set_node_ids(None, implicit_ids=True, num_nodes=indptr.size - 1)
+        mat = g.simulate_walks_array(1, 20)                 # builds thresholds + tables, walks immediately
+        thr = orc.noise_thresholds_csr(indptr, data, 0.3) if extend else None
+        alias = orc.alias_build(indptr, indices, data, 0.25, 4, extend, thr)
+        start = orc.shuffled_start(indptr.size - 1, 1, 5)
+        k = 6000
+        want = orc.walk_csr("PreComp", indptr, indices, data, 0.25, 4, start[:k], 20, alias=alias, rng=orc.RNG_PHILOX, seed=5)
+        assert np.array_equal(mat[:k], want), first_diff(mat[:k], want)
+        assert np.array_equal(g.alias_j, alias[1]) and np.array_equal(g.alias_q.view(np.uint32), alias[2].view(np.uint32))
+        assert np.array_equal(g.alias_indptr, alias[0])
+        g.release()
+
+
+def test_dropin_rebuilds_device_copy_when_the_graph_changes(mods):
+    """Round-1 advice: the cached engine must not outlive the arrays it was made from (the reference rebuilds its
+    closures on every call, pecanpy.py:143-144)."""
+    from pecanpy_b200 import pecanpy as b2
+    orc = mods["orc"]
+    a = load("w200_sparseotf_n2v")
+    b = load("hub400_sparseotf_n2v")
+    g = b2.PreComp(p=0.5, q=2, random_state=3)
+    for c in (a, b, a):
+        g.indptr, g.indices, g.data = c["indptr"], c["indices"], c["data"]
+        g.set_node_ids(None, implicit_ids=True, num_nodes=c["indptr"].size - 1)
+        mat = g.simulate_walks_array(2, 12)
+        start = orc.shuffled_start(g.num_nodes, 2, 3)
+        alias = orc.alias_build(c["indptr"], c["indices"], c["data"], 0.5, 2)
+        want = orc.walk_csr("PreComp", c["indptr"], c["indices"], c["data"], 0.5, 2, start, 12, alias=alias,
+                            rng=orc.RNG_PHILOX, seed=3)
+        assert np.array_equal(mat, want), first_diff(mat, want)
+    # re-weighting the same topology and changing p: tables must follow
+    g.data = (g.data * np.float32(1.5)).astype(np.float32)
+    g.p = 2.0
+    mat = g.simulate_walks_array(1, 10)
+    alias = orc.alias_build(g.indptr, g.indices, g.data, 2.0, 2)
+    want = orc.walk_csr("PreComp", g.indptr, g.indices, g.data, 2.0, 2, orc.shuffled_start(g.num_nodes, 1, 3), 10,
+                        alias=alias, rng=orc.RNG_PHILOX, seed=3)
+    assert np.array_equal(mat, want)
+    s = b2.SparseOTF(p=1, q=1, extend=True, gamma=0.0, random_state=1)
+    s.indptr, s.indices, s.data = a["indptr"], a["indices"], a["data"]
+    s.set_node_ids(None, implicit_ids=True, num_nodes=a["indptr"].size - 1)
+    t0 = s.get_noise_thresholds()
+    s.gamma = 1.0                                            # thresholds depend on gamma
+    m1 = s.simulate_walks_array(1, 8)
+    thr = orc.noise_thresholds_csr(a["indptr"], a["data"], 1.0)
+    want = orc.walk_csr("SparseOTF", a["indptr"], a["indices"], a["data"], 1, 1, orc.shuffled_start(s.num_nodes, 1, 1), 8,
+                        extend=True, thr=thr, rng=orc.RNG_PHILOX, seed=1)
+    assert np.array_equal(m1, want) and not np.array_equal(t0, thr)
+    g.release(); s.release()

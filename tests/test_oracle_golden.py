@@ -15,7 +15,7 @@ from oracle import oracle as orc
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 WALK_CASES = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN, "*.npz"))
-                    if not os.path.basename(f).startswith("probs_"))
+                    if not os.path.basename(f).startswith(("probs_", "graph_")))
 
 # test/test_walk.py:21-82 (ids a..e -> 0..4); PreCompFirstOrder row uses pecanpy.PreComp (:89)
 REFERENCE_KNOWN_ANSWERS = {
