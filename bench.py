@@ -303,10 +303,23 @@ def run_workload(name, args, K, W, rank, world, local_rank, *, do_e2e=True, do_c
     ld = L + 2
     # Row blocks.  One GPU: the whole array.  N GPUs: NB batches; batch b of rank r = rows [(b N + r) B, +B), so that
     # the all-gather of batch b fills the contiguous rows [b N B, (b + 1) N B) while batch b + 1 is being walked.
-    NB = 1 if world == 1 else max(1, min(args.batches, (tot + world * 65536 - 1) // (world * 65536)))
+    # (default: ONE batch = the single all-gather at the end; measured on 2 x B200, more batches only cost: every
+    # extra launch of the lane-per-walker kernel adds ~1.4 ms, more than the overlap hides -- DESIGN.md 5)
+    auto_nb = 1
+    NB = 1 if world == 1 else max(1, min(args.batches or auto_nb, (tot + world * 65536 - 1) // (world * 65536)))
     B = (tot + world * NB - 1) // (world * NB)
     tot_pad = B * world * NB
-    full = torch.zeros((tot_pad, ld), dtype=torch.int32, device=dev)
+    peer, gather = None, "none"
+    if world > 1:
+        gather = args.gather
+        if gather == "push":
+            from pecanpy_b200.dist import PeerMatrix
+            peer = PeerMatrix(tot_pad, ld, dev)             # collective; .ok is agreed between the ranks
+            if not peer.ok:                                 # no CUDA IPC / peer access on this box: NCCL does it
+                log(f"[bench] rank {rank}: peer mapping unavailable ({peer.error}); falling back to NCCL")
+                peer.close()
+                peer, gather = None, "nccl"
+    full = peer.full if peer is not None else torch.zeros((tot_pad, ld), dtype=torch.int32, device=dev)
     start_pad = np.zeros(tot_pad, dtype=np.uint32)
     start_pad[:tot] = start
     d_start_all = torch.from_numpy(start_pad.view(np.int32)).to(dev)
@@ -317,22 +330,27 @@ def run_workload(name, args, K, W, rank, world, local_rank, *, do_e2e=True, do_c
     my_rows = sum(r for _, r in blocks)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > L2 (126 MB)
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
-
     def one_pass(seed, events=None):
-        """Walk this rank's blocks; with N > 1 all-gather each batch on a side stream while the next one is walked."""
+        """Walk this rank's blocks.  N > 1: each walked batch leaves for the other ranks while the next one is being
+        walked -- pushed into the peers' matrices by the copy engines (CUDA IPC + DMA over NVLink), or, with
+        --gather nccl, all-gathered by NCCL on a side stream."""
         cur = torch.cuda.current_stream(dev)
         for b, (r0, rows) in enumerate(blocks):
             if rows:
                 eng.walk(wl["mode"], wl["p"], wl["q"], d_start_all[r0:r0 + rows], L, seed=seed, extend=wl["extend"],
                          row0=r0, out=full[r0:r0 + rows], flags=args.flags, collect_stats=False)
-            if world > 1:
+            if peer is not None:
+                peer.push(r0, r0 + rows)
+            elif world > 1:
                 comm.wait_stream(cur)
                 with torch.cuda.stream(comm):
                     seg = full[b * world * B:(b + 1) * world * B]
                     dist.all_gather_into_tensor(seg.view(-1), full[(b * world + rank) * B:(b * world + rank + 1) * B].view(-1))
         if events is not None:
             events[1].record(cur)                           # this rank's walk kernels are done
-        if world > 1:
+        if peer is not None:
+            peer.finish()
+        elif world > 1:
             cur.wait_stream(comm)
 
     for it in range(W):
@@ -343,6 +361,10 @@ def run_workload(name, args, K, W, rank, world, local_rank, *, do_e2e=True, do_c
         # one-time graph preparation (like the upload of the CSR): per-edge records + common-neighbour lists
         extras["edge_index_build_ms"] = eng.edge_index_ms
         extras["edge_index_bytes"] = 16 * (int(g["indptr"][-1]) + 1) + 4 * int(getattr(eng, "edge_index_words", 0))
+    if getattr(eng, "windex_ms", None) is not None:
+        extras["weighted_index_build_ms"] = eng.windex_ms
+        extras["weighted_index_bytes"] = eng.windex_bytes
+        extras["weighted_index_counts"] = eng.windex_counts
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -454,6 +476,9 @@ def run_workload(name, args, K, W, rank, world, local_rank, *, do_e2e=True, do_c
     # ---------------- e2e through the host-buffer C-ABI entry points: ONE host matrix
     e2e = None
     del full
+    if peer is not None:                                    # unmap the peers' matrices, then free the own one
+        peer.close()
+        peer = None
     torch.cuda.empty_cache()
     if do_e2e:
         e2e = run_e2e(torch, dist, eng, g, wl, start, L, K, rank, world, local_rank, steps_job, args)
@@ -475,7 +500,7 @@ def run_workload(name, args, K, W, rank, world, local_rank, *, do_e2e=True, do_c
         line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": 1e3 * t_total / max(K_eff, 1), "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": dtype_of(wl), "data": "synthetic",
-                "config": config_of(args, name, wl, g, world, NB), "clocks": clocks, "gpu_launches": launches,
+                "config": config_of(args, name, wl, g, world, NB, {"push": "copy engines over NVLink into CUDA-IPC mapped peer matrices", "nccl": "NCCL", "none": ""}[gather]), "clocks": clocks, "gpu_launches": launches,
                 "timed_passes": K_eff, "steps_per_pass": steps_job,
                 "kernel_ms_max_over_ranks": 1e3 * t_kernel_max / max(K_eff, 1),
                 "checksum": {"seed": CHECK_SEED, "fnv_like_u64": checksum},
@@ -562,7 +587,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the sub-benchmarks of the other BASELINE configs")
-    ap.add_argument("--batches", type=int, default=8, help="N > 1: all-gather batches overlapped with the walk")
+    ap.add_argument("--batches", type=int, default=0, help="N > 1: all-gather batches overlapped with the walk (0 = auto)")
+    ap.add_argument("--gather", default="nccl", choices=["push", "nccl"],
+                    help="N > 1: copy-engine pushes into the peers' matrices (CUDA IPC) or NCCL all-gather")
     ap.add_argument("--flags", type=int, default=0, help="b2w_walk flags (debug)")
     args = ap.parse_args()
 
@@ -652,13 +679,13 @@ def dtype_of(wl):
     return "f64" if wl["mode"] == "DenseOTF" else "f32"
 
 
-def config_of(args, name, wl, g, world, nb):
+def config_of(args, name, wl, g, world, nb, gather="none"):
     return {"workload": name, "baseline_config": wl.get("config"), "mode": wl["mode"], "p": wl["p"], "q": wl["q"],
             "extend": wl["extend"], "weighted": wl["weighted"],
             "num_nodes": g["n"], "nnz": int(g["indptr"][-1]) if g["kind"] == "csr" else None,
             "num_walks": wl["num_walks"], "walk_length": wl["L"], "rng": "philox4x32-10 keyed by (seed, global row, step)",
-            "parallelism": (f"graph replicated, walkers sharded over {world} GPU(s), {nb} all-gather batch(es) over NCCL "
-                            "overlapped with the walk of the next batch") if world > 1 else "1 GPU",
+            "parallelism": (f"graph replicated, walkers sharded over {world} GPU(s), all-gather in {nb} batch(es) "
+                            f"overlapped with the walk of the next batch ({gather})") if world > 1 else "1 GPU",
             "l2": "256 MiB buffer written between timed iterations (L2 flush); graph+walk matrix exceed L2",
             "scale": args.scale}
 

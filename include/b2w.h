@@ -86,6 +86,7 @@ typedef struct {
 #define B2W_GRAPH_UNWEIGHTED 0x4u /* every stored weight == 1.0f */
 #define B2W_GRAPH_HAS_ALIAS 0x8u
 #define B2W_GRAPH_HAS_EDGE_INDEX 0x10u
+#define B2W_GRAPH_HAS_WINDEX 0x20u /* weighted per-edge index attached (valid for the p, q, extend it was built with) */
 
 typedef struct {
   uint64_t steps;            /* walk steps taken (sum of effective_length - 1)           */
@@ -218,6 +219,31 @@ int b2w_edge_index_finish(b2w_graph* g, void* d_rec, uint32_t* d_tri, uint64_t t
                           size_t work_bytes, void* stream);
 int b2w_graph_set_edge_index(b2w_graph* g, const void* d_rec, const uint32_t* d_tri, uint64_t tri_words);
 
+/* ---- weighted per-edge index (SparseOTF on weighted graphs, node2vec+, any p and q) ------------------------
+ * The biased weights of a step taken after arriving over a stored edge (rw/sparse_rw.py:51-130) are a function of the
+ * edge and of (p, q, node2vec+ thresholds).  Prepared once per (graph, parameters), they turn the step into
+ * O(log deg) arithmetic for one lane: per row the BASE biased weights (slot neither prev nor common) and their f64
+ * prefix sums; per edge a 32-byte record (next node, degree, row start, position and weight of the return edge, the
+ * reference's exact f32 normaliser of that step), the common neighbours whose weight deviates from the base
+ * ("exceptions": position, exact f32 weight, f64 prefix of the deviations) and, for rows of >= 128 slots, checkpoints
+ * of the reference's exact f32 cdf every 128 positions (so that the rare exact replay is bounded).  Walks are
+ * bit-identical with and without it.  Caller-owned arrays:
+ *     d_rec   32 bytes x (nnz + 1), 32-byte aligned        d_bw  float[nnz]        d_bq  double[nnz]
+ *     d_exc   24 bytes x exc_entries                       d_ckpt float[ckpt_floats]
+ * b2w_windex_prepare fills d_rec / d_bw / d_bq and reports the two data-dependent sizes (synchronous;
+ * B2W_ERR_UNSUPPORTED when they do not fit 32-bit offsets); b2w_windex_finish fills d_exc / d_ckpt, computes the
+ * normalisers and attaches the index (borrowed until b2w_graph_clear_windex / destroy; synchronous).  d_work: at least
+ * b2w_windex_work_bytes(g) bytes, the SAME untouched buffer in both calls.  b2w_walk uses the index when mode, p, q,
+ * extend and the d_thr pointer are the ones it was built with (B2W_FLAG_NO_EDGE_INDEX: never). */
+size_t b2w_windex_work_bytes(const b2w_graph* g);
+int b2w_windex_prepare(const b2w_graph* g, double p, double q, int extend, const float* d_thr, void* d_rec, float* d_bw,
+                       double* d_bq, void* d_work, size_t work_bytes, uint64_t* h_exc_entries, uint64_t* h_ckpt_floats,
+                       void* stream);
+int b2w_windex_finish(b2w_graph* g, double p, double q, int extend, const float* d_thr, void* d_rec, float* d_bw,
+                      double* d_bq, void* d_exc, uint64_t exc_entries, float* d_ckpt, uint64_t ckpt_floats, void* d_work,
+                      size_t work_bytes, void* stream);
+int b2w_graph_clear_windex(b2w_graph* g);
+
 /* ---- the walk kernel -------------------------------------------------------------------
  * Replaces Base._random_walks (pecanpy.py:164-210) together with the move_forward closure of
  * `mode`.  Walks rows [row0, row0 + n_rows) of the caller's (host-shuffled, pecanpy.py:135-141)
@@ -264,6 +290,25 @@ int b2w_walk_host(const b2w_graph* g, int mode, double p, double q, int extend, 
 int b2w_walk_multi(int n_graphs, b2w_graph* const* graphs, int mode, double p, double q, int extend,
                    const float* const* d_thr, const uint32_t* h_start, uint64_t n_rows, uint32_t walk_length,
                    uint64_t seed, uint32_t* h_out, uint64_t batch_rows, b2w_walk_stats* h_stats, uint32_t flags);
+
+/* ---- one-node all-gather by the copy engines (multi-process jobs, one rank per GPU) ----------------------
+ * Replaces the trailing ncclAllGather of SURVEY.md 8b/8e where it has to OVERLAP with the walk: the walk kernels fill
+ * the chip, a collective that runs kernels beside them slows them down; device-to-device DMA does not.
+ *   b2w_shared_alloc  cudaMalloc of the rank's full-size walk matrix + its 64-byte IPC handle (exchange the handles
+ *                     between the ranks with any host-side channel, e.g. torch.distributed.all_gather_object)
+ *   b2w_shared_open   map a PEER's matrix from its handle into this process, from THIS rank's device (peer access
+ *                     over NVLink is enabled lazily; nothing runs on the peer GPU)
+ *   b2w_push_rows     rows [row_lo, row_lo + rows) of d_peers[self] -> the same rows of every other d_peers[p]:
+ *                     one cudaMemcpyAsync per peer on `stream` (order it after the walk of those rows; use a side
+ *                     stream so that the next batch's walk overlaps)
+ *   b2w_shared_close / b2w_shared_free   unmap a peer's matrix / free the own one (unmap everywhere first).
+ * After a rank has synchronised its push stream AND a barrier between the ranks, its matrix holds every row. */
+int b2w_shared_alloc(int device, size_t bytes, void** d_ptr, unsigned char handle[64]);
+int b2w_shared_free(int device, void* d_ptr);
+int b2w_shared_open(int device, const unsigned char handle[64], void** d_ptr);
+int b2w_shared_close(int device, void* d_ptr);
+int b2w_push_rows(int device, void* const* d_peers, int n_peers, int self, uint64_t row_lo, uint64_t rows,
+                  uint64_t row_bytes, void* stream);
 
 /* Sum of (effective_length - 1) over the rows of a device walk matrix (the metric's unit). */
 int b2w_count_steps(const uint32_t* d_out, uint64_t n_rows, uint32_t walk_length, uint64_t ld_out,

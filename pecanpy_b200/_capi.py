@@ -30,6 +30,7 @@ def FLAG_GROUP(n: int) -> int:
     return (n & 0xFF) << 8
 
 GRAPH_CSR, GRAPH_DENSE, GRAPH_UNWEIGHTED, GRAPH_HAS_ALIAS, GRAPH_HAS_EDGE_INDEX = 0x1, 0x2, 0x4, 0x8, 0x10
+GRAPH_HAS_WINDEX = 0x20
 
 EXPORTS = [
     "b2w_version", "b2w_last_error", "b2w_device_count", "b2w_graph_csr_create", "b2w_graph_dense_create",
@@ -37,6 +38,8 @@ EXPORTS = [
     "b2w_alias_build_first_order", "b2w_graph_set_alias", "b2w_walk_work_bytes", "b2w_walk", "b2w_walk_host",
     "b2w_count_steps", "b2w_philox_selftest", "b2w_walk_kernel_name", "b2w_noise_thresholds", "b2w_csr_from_edges_work_bytes", "b2w_csr_from_edges",
     "b2w_edgelist_parse", "b2w_edgelist_fetch", "b2w_edgelist_free",
+    "b2w_windex_work_bytes", "b2w_windex_prepare", "b2w_windex_finish", "b2w_graph_clear_windex",
+    "b2w_shared_alloc", "b2w_shared_free", "b2w_shared_open", "b2w_shared_close", "b2w_push_rows",
     "b2w_walk_multi", "b2w_alias_build_packed", "b2w_graph_set_alias_packed",
     "b2w_edge_index_work_bytes", "b2w_edge_index_prepare", "b2w_edge_index_finish", "b2w_graph_set_edge_index",
 ]
@@ -90,6 +93,16 @@ def lib():
     L.b2w_walk_host.argtypes = [vp, i32, dbl, dbl, i32, vp, vp, u64, u64, u32, u64, vp, u64, C.POINTER(WalkStats), u32]
     L.b2w_walk_multi.argtypes = [i32, C.POINTER(vp), i32, dbl, dbl, i32, C.POINTER(vp), vp, u64, u32, u64, vp, u64,
                                  C.POINTER(WalkStats), u32]
+    L.b2w_windex_work_bytes.argtypes = [vp]
+    L.b2w_windex_work_bytes.restype = sz
+    L.b2w_windex_prepare.argtypes = [vp, dbl, dbl, i32, vp, vp, vp, vp, vp, sz, C.POINTER(u64), C.POINTER(u64), vp]
+    L.b2w_windex_finish.argtypes = [vp, dbl, dbl, i32, vp, vp, vp, vp, vp, u64, vp, u64, vp, sz, vp]
+    L.b2w_graph_clear_windex.argtypes = [vp]
+    L.b2w_shared_alloc.argtypes = [i32, sz, C.POINTER(vp), C.c_char_p]
+    L.b2w_shared_free.argtypes = [i32, vp]
+    L.b2w_shared_open.argtypes = [i32, C.c_char_p, C.POINTER(vp)]
+    L.b2w_shared_close.argtypes = [i32, vp]
+    L.b2w_push_rows.argtypes = [i32, C.POINTER(vp), i32, i32, u64, u64, u64, vp]
     L.b2w_walk_kernel_name.argtypes = [vp, i32, dbl, dbl, i32, u32]
     L.b2w_walk_kernel_name.restype = C.c_char_p
     L.b2w_noise_thresholds.argtypes = [vp, dbl, vp, vp]

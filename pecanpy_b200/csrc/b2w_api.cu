@@ -337,6 +337,10 @@ extern "C" int b2w_walk(const b2w_graph* g, int mode, double p, double q, int ex
         return b2w_launch_uw_edge(g, P, s);
       return b2w_launch_uw(g, P, s);
     }
+    // weighted graphs / node2vec+ / any p, q: the weighted per-edge index built for exactly these parameters
+    if (!(flags & (B2W_FLAG_NO_EDGE_INDEX | B2W_FLAG_NO_UNWEIGHTED_KERNEL | B2W_FLAG_COOP)) && !((flags >> 8) & 0xFF) &&
+        b2w_windex_matches(g, p, q, ext, d_thr))
+      return b2w_launch_wedge(g, P, s);
     return b2w_launch_sparse_warp(g, P, s);
   }
   if (mode == B2W_MODE_PRECOMP_FIRST_ORDER && g->alias_qj) {
@@ -365,6 +369,9 @@ extern "C" const char* b2w_walk_kernel_name(const b2w_graph* g, int mode, double
           return "walk_uw_edge_kernel";
         return "walk_uw_kernel";
       }
+      if (!(flags & (B2W_FLAG_NO_EDGE_INDEX | B2W_FLAG_NO_UNWEIGHTED_KERNEL | B2W_FLAG_COOP)) && !((flags >> 8) & 0xFF) &&
+          (g->flags & B2W_GRAPH_HAS_WINDEX) && g->w_p == p && g->w_q == q && g->w_extend == (extend ? 1 : 0))
+        return "walk_wedge_kernel";
       return "walk_sparse_warp_kernel";
   }
   return "";

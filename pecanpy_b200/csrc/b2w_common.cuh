@@ -32,6 +32,15 @@ struct b2w_graph {
   const void* edge_rec;
   const uint32_t* edge_tri;
   uint64_t edge_tri_words;
+  // weighted per-edge index (borrowed; b2w_wedge.cu), valid for the bias parameters it was built with
+  const void* w_rec;
+  const void* w_exc;
+  const float* w_bw;
+  const double* w_bq;
+  const float* w_ckpt;
+  const float* w_thr;
+  double w_p, w_q;
+  int w_extend;
   // staging buffers / streams of b2w_walk_host (lazily allocated, guarded by their own mutex)
   b2w_host_pipe* pipe;
 };
@@ -164,5 +173,7 @@ size_t b2w_uw_work_bytes(const b2w_graph* g);
 int b2w_launch_uw(const b2w_graph* g, const WalkParams& P, cudaStream_t s);
 int b2w_launch_uw_edge(const b2w_graph* g, const WalkParams& P, cudaStream_t s);
 int b2w_launch_precomp_edge(const b2w_graph* g, const WalkParams& P, cudaStream_t s);
+int b2w_launch_wedge(const b2w_graph* g, const WalkParams& P, cudaStream_t s);
+bool b2w_windex_matches(const b2w_graph* g, double p, double q, int extend, const float* d_thr);
 bool b2w_uw_grid(const b2w_graph* g, double p, double q, int* grid_exp);
 uint32_t b2w_sparse_warp_total_warps(const b2w_graph* g);

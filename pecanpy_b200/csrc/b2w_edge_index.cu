@@ -24,6 +24,7 @@
 // prefix-sums the list lengths and reports the number of list words; the caller allocates them;
 // b2w_edge_index_finish fills the lists and attaches the index to the handle.
 #include "b2w_membership.cuh"
+#include "b2w_scan.cuh"
 
 namespace {
 
@@ -31,7 +32,6 @@ constexpr uint32_t KPF_POS_MASK = 0x3FFFFFFFu;
 constexpr uint32_t KPF_NOTFOUND = 0x40000000u;
 constexpr uint32_t KPF_HAS_TRI = 0x80000000u;
 constexpr int EI_THREADS = 256;
-constexpr int SCAN_ITEMS = 16;                                       // per thread -> 4096 records per block
 
 // src[e] = owner row of CSR slot e (one warp per row, coalesced)
 __global__ void __launch_bounds__(EI_THREADS) edge_src_kernel(const uint32_t n, const uint32_t* __restrict__ indptr,
@@ -132,93 +132,13 @@ __global__ void __launch_bounds__(EI_THREADS) edge_index_kernel(const uint32_t n
   }
 }
 
-// ---- exclusive prefix sum of rec[e].z (list words) in place: block sums -> one-block scan -> block-local scan
-__global__ void __launch_bounds__(EI_THREADS) scan_block_sums(const uint64_t count, const uint4* __restrict__ rec,
-                                                              unsigned long long* __restrict__ sums) {
-  __shared__ unsigned long long s_w[EI_THREADS / 32];
-  const uint64_t base = (uint64_t)blockIdx.x * EI_THREADS * SCAN_ITEMS;
-  unsigned long long acc = 0;
-  for (int it = 0; it < SCAN_ITEMS; ++it) {
-    const uint64_t e = base + (uint64_t)it * EI_THREADS + threadIdx.x;
-    if (e < count) acc += reinterpret_cast<const uint32_t*>(rec + e)[2];
-  }
-  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(B2W_FULL, acc, o);
-  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long t = 0;
-    for (int w = 0; w < EI_THREADS / 32; ++w) t += s_w[w];
-    sums[blockIdx.x] = t;
-  }
-}
-
-__global__ void __launch_bounds__(1024) scan_sums_kernel(const uint64_t nblocks, unsigned long long* __restrict__ sums,
-                                                         unsigned long long* __restrict__ total) {
-  // one block; every thread owns a contiguous slice
-  __shared__ unsigned long long s_part[1024];
-  const uint64_t per = (nblocks + 1023) / 1024;
-  const uint64_t lo = min(nblocks, (uint64_t)threadIdx.x * per), hi = min(nblocks, lo + per);
-  unsigned long long acc = 0;
-  for (uint64_t i = lo; i < hi; ++i) acc += sums[i];
-  s_part[threadIdx.x] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned long long run = 0;
-    for (int t = 0; t < 1024; ++t) { const unsigned long long v = s_part[t]; s_part[t] = run; run += v; }
-    *total = run;
-  }
-  __syncthreads();
-  unsigned long long run = s_part[threadIdx.x];
-  for (uint64_t i = lo; i < hi; ++i) { const unsigned long long v = sums[i]; sums[i] = run; run += v; }
-}
-
-__global__ void __launch_bounds__(EI_THREADS) scan_apply_kernel(const uint64_t count, uint4* __restrict__ rec,
-                                                                const unsigned long long* __restrict__ sums) {
-  // items are laid out [it][thread] inside the block, so the block-local order is it-major
-  __shared__ uint32_t s_warp[SCAN_ITEMS][EI_THREADS / 32];
-  __shared__ uint32_t s_itbase[SCAN_ITEMS];
-  const uint64_t base = (uint64_t)blockIdx.x * EI_THREADS * SCAN_ITEMS;
-  const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  uint32_t v[SCAN_ITEMS], incl[SCAN_ITEMS];
-#pragma unroll
-  for (int it = 0; it < SCAN_ITEMS; ++it) {
-    const uint64_t e = base + (uint64_t)it * EI_THREADS + threadIdx.x;
-    v[it] = e < count ? reinterpret_cast<const uint32_t*>(rec + e)[2] : 0u;
-    uint32_t x = v[it];
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(B2W_FULL, x, o); if (lane >= (uint32_t)o) x += y; }
-    incl[it] = x;
-    if (lane == 31) s_warp[it][wib] = x;
-  }
-  __syncthreads();
-  if (threadIdx.x < SCAN_ITEMS) {
-    uint32_t run = 0;
-    for (int w = 0; w < EI_THREADS / 32; ++w) { const uint32_t t = s_warp[threadIdx.x][w]; s_warp[threadIdx.x][w] = run; run += t; }
-    s_itbase[threadIdx.x] = run;                                      // total of this item row
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t run = 0;
-    for (int it = 0; it < SCAN_ITEMS; ++it) { const uint32_t t = s_itbase[it]; s_itbase[it] = run; run += t; }
-  }
-  __syncthreads();
-  const uint32_t blockbase = (uint32_t)sums[blockIdx.x];              // total < 2^32 was checked by the caller
-#pragma unroll
-  for (int it = 0; it < SCAN_ITEMS; ++it) {
-    const uint64_t e = base + (uint64_t)it * EI_THREADS + threadIdx.x;
-    if (e < count) reinterpret_cast<uint32_t*>(rec + e)[2] = blockbase + s_itbase[it] + s_warp[it][wib] + incl[it] - v[it];
-  }
-}
-
-uint64_t scan_blocks(uint64_t count) { return (count + (uint64_t)EI_THREADS * SCAN_ITEMS - 1) / ((uint64_t)EI_THREADS * SCAN_ITEMS); }
-
 size_t src_bytes(const b2w_graph* g) { return (((size_t)g->nnz + 1) * sizeof(uint32_t) + 255) & ~(size_t)255; }
 
 }  // namespace
 
 extern "C" size_t b2w_edge_index_work_bytes(const b2w_graph* g) {
   if (!g || !(g->flags & B2W_GRAPH_CSR)) return 0;
-  return src_bytes(g) + (scan_blocks(g->nnz + 1) + 2) * sizeof(unsigned long long) + 256;
+  return src_bytes(g) + b2w_scan::work_bytes(g->nnz + 1) + 256;
 }
 
 static int check_args(const b2w_graph* g, const void* d_rec, const char* what) {
@@ -241,23 +161,17 @@ extern "C" int b2w_edge_index_prepare(const b2w_graph* g, void* d_rec, void* d_w
   uint32_t* src = reinterpret_cast<uint32_t*>(d_work);
   unsigned long long* sums = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(d_work) + src_bytes(g));
   const uint64_t count = g->nnz + 1;
-  const uint64_t nb = scan_blocks(count);
-  unsigned long long* total = sums + nb;
   const unsigned grid = (unsigned)g->num_sms * 8;
   edge_src_kernel<<<grid, EI_THREADS, 0, s>>>(g->n, g->indptr, src);
   edge_index_kernel<false><<<grid, EI_THREADS, 0, s>>>(g->n, g->nnz, g->indptr, g->indices, src, reinterpret_cast<uint4*>(d_rec), nullptr);
-  scan_block_sums<<<(unsigned)nb, EI_THREADS, 0, s>>>(count, reinterpret_cast<const uint4*>(d_rec), sums);
-  scan_sums_kernel<<<1, 1024, 0, s>>>(nb, sums, total);
   B2W_CUDA(cudaGetLastError());
   unsigned long long h_total = 0;
-  B2W_CUDA(cudaMemcpyAsync(&h_total, total, sizeof h_total, cudaMemcpyDeviceToHost, s));
-  B2W_CUDA(cudaStreamSynchronize(s));
+  B2W_CUDA(b2w_scan::exclusive_scan(count, reinterpret_cast<uint32_t*>(d_rec) + 2, 4, sums, &h_total, s));   // field .z of uint4
   *h_tri_words = h_total;
   if (h_total >= 0xFFFFFFFFull) {
     b2w_set_error("b2w_edge_index_prepare: %llu list words do not fit 32-bit offsets (use the on-the-fly kernels)", h_total);
     return B2W_ERR_UNSUPPORTED;
   }
-  scan_apply_kernel<<<(unsigned)nb, EI_THREADS, 0, s>>>(count, reinterpret_cast<uint4*>(d_rec), sums);
   return b2w_cuda_fail(cudaGetLastError(), "edge index prepare");
 }
 

@@ -64,6 +64,8 @@ class WalkEngine:
         self.edge_index_policy = os.environ.get("B2W_EDGE_INDEX", "auto")
         self.edge_index_ms: Optional[float] = None
         self._edge_index_failed = False
+        self.windex_ms: Optional[float] = None
+        self._windex_key = None
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -182,6 +184,60 @@ class WalkEngine:
         self.edge_index_words = int(words.value)
         return True
 
+    def build_windex(self, p: float, q: float, extend: bool = False) -> bool:
+        """Build the WEIGHTED per-edge index for these bias parameters (b2w_windex_prepare / _finish) and attach it:
+        SparseOTF on weighted graphs, node2vec+ and arbitrary p, q then run the lane-per-walker kernel of
+        b2w_wedge.cu.  Returns False (the weight-streaming kernel stays in charge) when it does not fit."""
+        if self.kind != "csr":
+            raise ValueError("the weighted edge index needs a CSR graph")
+        if extend and self.thr is None:
+            raise ValueError("extend=True needs set_thresholds() / compute_thresholds() first")
+        gi = self.info()
+        key = (float(p), float(q), bool(extend), self.thr.data_ptr() if extend else 0)
+        if gi.flags & capi.GRAPH_HAS_WINDEX and self._windex_key == key:
+            return True
+        self.drop_windex()
+        with torch.cuda.device(self.device):
+            free, _ = torch.cuda.mem_get_info(self.device)
+            nnz = int(gi.nnz)
+            wb = int(self.lib.b2w_windex_work_bytes(self.handle))
+            if 44 * (nnz + 1) + wb > 0.5 * free:
+                return False
+            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            t0.record()
+            rec = torch.empty(8 * (nnz + 1), dtype=torch.int32, device=self.device)
+            bw = torch.empty(max(nnz, 1), dtype=torch.float32, device=self.device)
+            bq = torch.empty(max(nnz, 1), dtype=torch.float64, device=self.device)
+            work = torch.empty(wb, dtype=torch.uint8, device=self.device)
+            n_exc, n_ck = C.c_uint64(0), C.c_uint64(0)
+            thr = _ptr(self.thr if extend else None)
+            rc = self.lib.b2w_windex_prepare(self.handle, float(p), float(q), int(bool(extend)), thr, _ptr(rec), _ptr(bw),
+                                             _ptr(bq), _ptr(work), wb, C.byref(n_exc), C.byref(n_ck), C.c_void_p(stream))
+            if rc == capi.ERR_UNSUPPORTED or (rc == capi.OK and 24 * n_exc.value + 4 * n_ck.value > 0.5 * free):
+                return False
+            capi.check(rc, "b2w_windex_prepare")
+            exc = torch.empty(3 * max(int(n_exc.value), 1), dtype=torch.int64, device=self.device)
+            ck = torch.empty(max(int(n_ck.value), 1), dtype=torch.float32, device=self.device)
+            capi.check(self.lib.b2w_windex_finish(self.handle, float(p), float(q), int(bool(extend)), thr, _ptr(rec),
+                                                  _ptr(bw), _ptr(bq), _ptr(exc), int(n_exc.value), _ptr(ck),
+                                                  int(n_ck.value), _ptr(work), wb, C.c_void_p(stream)), "b2w_windex_finish")
+            t1.record()
+            t1.synchronize()
+            self.windex_ms = t0.elapsed_time(t1)
+        self._keep["w_rec"], self._keep["w_bw"], self._keep["w_bq"], self._keep["w_exc"], self._keep["w_ckpt"] = rec, bw, bq, exc, ck
+        self._windex_key = key
+        self.windex_bytes = 32 * (nnz + 1) + 12 * nnz + 24 * int(n_exc.value) + 4 * int(n_ck.value)
+        self.windex_counts = dict(exceptions=int(n_exc.value), checkpoints=int(n_ck.value))
+        return True
+
+    def drop_windex(self):
+        if self.kind == "csr" and self.handle:
+            capi.check(self.lib.b2w_graph_clear_windex(self.handle), "b2w_graph_clear_windex")
+        for k in ("w_rec", "w_bw", "w_bq", "w_exc", "w_ckpt"):
+            self._keep.pop(k, None)
+        self._windex_key = None
+
     def drop_edge_index(self):
         if self.kind == "csr" and self.handle:
             capi.check(self.lib.b2w_graph_set_edge_index(self.handle, None, None, 0), "b2w_graph_set_edge_index")
@@ -193,13 +249,17 @@ class WalkEngine:
         exactly representable biases; PreComp)."""
         if self.kind != "csr" or self.edge_index_policy in ("0", "off", "never") or self._edge_index_failed:
             return
-        if flags & capi.FLAG_NO_EDGE_INDEX or self.has_edge_index:
+        if flags & capi.FLAG_NO_EDGE_INDEX:
             return
-        want = mode == capi.MODE_PRECOMP
-        if mode == capi.MODE_SPARSE_OTF and not extend:
-            name = self.lib.b2w_walk_kernel_name(self.handle, mode, float(p), float(q), 0, int(flags)).decode()
-            want = name == "walk_uw_kernel"
-        if want:
+        if mode == capi.MODE_SPARSE_OTF:
+            name = self.lib.b2w_walk_kernel_name(self.handle, mode, float(p), float(q), int(bool(extend)), int(flags)).decode()
+            if name == "walk_uw_kernel" and not self.has_edge_index:
+                self.build_edge_index()
+            elif name == "walk_sparse_warp_kernel" and not (flags & (capi.FLAG_NO_UNWEIGHTED_KERNEL | capi.FLAG_COOP | 0xFF00)):
+                # weighted graph / node2vec+ / biases off the exact grid: the weighted index for THESE parameters
+                if not extend or self.thr is not None:
+                    self.build_windex(p, q, extend)
+        elif mode == capi.MODE_PRECOMP and not self.has_edge_index:
             self.build_edge_index()
 
     def _scratch(self, key: str, nbytes: int) -> Optional[torch.Tensor]:

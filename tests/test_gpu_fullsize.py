@@ -147,3 +147,31 @@ def test_full_size_dense_config5():
     want = orc.walk_dense(data, nz, 0.5, 2.0, start[:k], L, extend=True, thr=want_thr, rng=orc.RNG_PHILOX, seed=13)
     assert np.array_equal(a[:k].cpu().numpy().view(np.uint32), want)
     eng.close()
+
+
+@pytest.mark.parametrize("extend", [False, True], ids=["n2v", "n2v+"])
+def test_full_size_weighted_sparse_otf(extend):
+    """BASELINE config #3's topology with random weights, one walk per node (10^6 walkers): the weighted edge-index
+    kernel and the weight-streaming kernel give IDENTICAL matrices; a prefix equals the oracle."""
+    import torch
+    from oracle import oracle as orc
+    from pecanpy_b200 import synth
+    from pecanpy_b200.engine import WalkEngine
+    indptr, indices, data = synth.power_law_csr(1_000_000, 10_000_000, seed=1, weighted=True)
+    p, q, L = 4.0, 0.25, 80
+    start = synth.shuffled_start(1_000_000, 1, 0)
+    eng = WalkEngine.from_csr(indptr, indices, data, device="cuda:0")
+    thr = eng.compute_thresholds(0.0).cpu().numpy() if extend else None
+    a = eng.walk("SparseOTF", p, q, start, L, seed=5, extend=extend)
+    assert eng.kernel_name("SparseOTF", p, q, extend) == "walk_wedge_kernel"
+    st = eng.stats()
+    b = eng.walk("SparseOTF", p, q, start, L, seed=5, extend=extend, flags=0x40)
+    assert eng.kernel_name("SparseOTF", p, q, extend, flags=0x40) == "walk_sparse_warp_kernel"
+    assert torch.equal(a, b), "weighted edge-index kernel and weight-streaming kernel disagree at full size"
+    assert st["steps"] == eng.count_steps(a, L)
+    assert _check_rows_are_walks(torch, torch.device("cuda", 0), indptr, indices, a, L) <= st["overflow_choices"]
+    k = 10000
+    want = orc.walk_csr("SparseOTF", indptr, indices, data, p, q, start[:k], L, extend=extend, thr=thr,
+                        rng=orc.RNG_PHILOX, seed=5)
+    assert np.array_equal(a[:k].cpu().numpy().view(np.uint32), want)
+    eng.close()

@@ -90,7 +90,7 @@ def _free_port():
     return p
 
 
-def _rank_main(rank, world, port, batches, q):
+def _rank_main(rank, world, port, batches, gather, q):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -106,7 +106,9 @@ def _rank_main(rank, world, port, batches, q):
     indptr, indices, data = _graph()
     eng = WalkEngine.from_csr(indptr, indices, data, device=dev)
     start = orc.shuffled_start(20000, 2, 5)[:33333]
-    full = simulate_walks_distributed(eng, "SparseOTF", 4.0, 0.25, start, 30, seed=21, batches=batches)
+    if gather == "push" and ndev < world:
+        gather = "nccl"                                     # the peers' matrices are on the same device: nothing to map
+    full = simulate_walks_distributed(eng, "SparseOTF", 4.0, 0.25, start, 30, seed=21, batches=batches, gather=gather)
     torch.cuda.synchronize()
     q.put((rank, backend, eng.kernel_name("SparseOTF", 4.0, 0.25), full.cpu().numpy().view(np.uint32).copy()))
     dist.barrier()
@@ -114,8 +116,8 @@ def _rank_main(rank, world, port, batches, q):
     eng.close()
 
 
-@pytest.mark.parametrize("batches", [1, 4])
-def test_two_ranks_cuda_walks_equal_single_rank(batches):
+@pytest.mark.parametrize("batches,gather", [(1, "nccl"), (4, "nccl"), (3, "push")])
+def test_two_ranks_cuda_walks_equal_single_rank(batches, gather):
     """CUDA kernels on two ranks (row0 offsets, batch-interleaved blocks, all-gather): every rank's matrix equals
     the one-rank matrix and the oracle."""
     import torch.multiprocessing as mp
@@ -131,7 +133,7 @@ def test_two_ranks_cuda_walks_equal_single_rank(batches):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, batches, q)) for r in range(2)]
+    procs = [ctx.Process(target=_rank_main, args=(r, 2, port, batches, gather, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]
