@@ -361,6 +361,9 @@ def run_workload(name, args, K, W, rank, world, local_rank, *, do_e2e=True, do_c
         # one-time graph preparation (like the upload of the CSR): per-edge records + common-neighbour lists
         extras["edge_index_build_ms"] = eng.edge_index_ms
         extras["edge_index_bytes"] = 16 * (int(g["indptr"][-1]) + 1) + 4 * int(getattr(eng, "edge_index_words", 0))
+    if getattr(eng, "edge_ckpt_ms", None) is not None:
+        extras["edge_ckpt_build_ms"] = eng.edge_ckpt_ms
+        extras["edge_ckpt_bytes"] = 4 * eng.edge_ckpt_floats
     if getattr(eng, "windex_ms", None) is not None:
         extras["weighted_index_build_ms"] = eng.windex_ms
         extras["weighted_index_bytes"] = eng.windex_bytes

@@ -70,6 +70,9 @@ typedef enum {
 #define B2W_FLAG_NO_TMA 0x10u /* DenseOTF: per-lane vector loads instead of cp.async.bulk staging */
 #define B2W_FLAG_COOP 0x20u /* unweighted SparseOTF, G < 32: warp-cooperative state-machine kernel (long rows by all 32 lanes) */
 #define B2W_FLAG_NO_EDGE_INDEX 0x40u /* unweighted SparseOTF / PreComp: ignore an attached edge index (on-the-fly membership kernels) */
+#define B2W_FLAG_NO_CKPT 0x80u /* unweighted SparseOTF through the edge index: replay from the start of the row, not from a checkpoint */
+#define B2W_FLAG_OFFEDGE_WARP 0x1000000u /* edge-index kernels: converged warps, steps without an edge by the whole warp (default on graphs with rows > 256) */
+#define B2W_FLAG_OFFEDGE_LANE 0x2000000u /* edge-index kernels: plain per-lane loops, steps without an edge by their own lane */
 #define B2W_FLAG_GROUP(n) (((uint32_t)(n) & 0xFFu) << 8) /* tuning: lanes per walker (8/16/32), 0 = auto */
 
 typedef struct b2w_graph b2w_graph; /* opaque */
@@ -218,6 +221,21 @@ int b2w_edge_index_prepare(const b2w_graph* g, void* d_rec, void* d_work, size_t
 int b2w_edge_index_finish(b2w_graph* g, void* d_rec, uint32_t* d_tri, uint64_t tri_words, void* d_work,
                           size_t work_bytes, void* stream);
 int b2w_graph_set_edge_index(b2w_graph* g, const void* d_rec, const uint32_t* d_tri, uint64_t tri_words);
+
+/* Checkpoints for the exact replay of the unweighted SparseOTF kernel (optional, per (p, q)): the ~1 % of the steps
+ * whose filter is inconclusive replay the reference's sequential f32 cumsum; on hub rows that is long, and walkers
+ * circulating among hubs do it every step.  For every stored edge (prev -> cur) with deg(cur) >= 128 whose reverse
+ * edge exists, the exact f32 cdf after elements 127, 255, ... of row(cur) is kept (float[deg(cur)][deg(cur) / 128] per
+ * such node), so a replay starts at most 128 positions before the answer.
+ *   b2w_edge_ckpt_prepare  d_ckb uint32[n + 1] <- per-node block offsets; *h_ckpt_floats = floats to allocate
+ *   b2w_edge_ckpt_finish   fills d_ckpt for (p, q) and attaches it (borrowed; used by walks with the same p, q)
+ * Needs the edge index attached; synchronous; d_work >= b2w_edge_ckpt_work_bytes(g). */
+size_t b2w_edge_ckpt_work_bytes(const b2w_graph* g);
+int b2w_edge_ckpt_prepare(const b2w_graph* g, uint32_t* d_ckb, void* d_work, size_t work_bytes, uint64_t* h_ckpt_floats,
+                          void* stream);
+int b2w_edge_ckpt_finish(b2w_graph* g, double p, double q, const uint32_t* d_ckb, float* d_ckpt, uint64_t ckpt_floats,
+                         void* stream);
+int b2w_graph_clear_edge_ckpt(b2w_graph* g);
 
 /* ---- weighted per-edge index (SparseOTF on weighted graphs, node2vec+, any p and q) ------------------------
  * The biased weights of a step taken after arriving over a stored edge (rw/sparse_rw.py:51-130) are a function of the

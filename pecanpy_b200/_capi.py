@@ -24,6 +24,9 @@ FLAG_NO_UNWEIGHTED_KERNEL = 0x8
 FLAG_NO_TMA = 0x10
 FLAG_COOP = 0x20
 FLAG_NO_EDGE_INDEX = 0x40
+FLAG_NO_CKPT = 0x80
+FLAG_OFFEDGE_WARP = 0x1000000
+FLAG_OFFEDGE_LANE = 0x2000000
 
 
 def FLAG_GROUP(n: int) -> int:
@@ -38,6 +41,7 @@ EXPORTS = [
     "b2w_alias_build_first_order", "b2w_graph_set_alias", "b2w_walk_work_bytes", "b2w_walk", "b2w_walk_host",
     "b2w_count_steps", "b2w_philox_selftest", "b2w_walk_kernel_name", "b2w_noise_thresholds", "b2w_csr_from_edges_work_bytes", "b2w_csr_from_edges",
     "b2w_edgelist_parse", "b2w_edgelist_fetch", "b2w_edgelist_free",
+    "b2w_edge_ckpt_work_bytes", "b2w_edge_ckpt_prepare", "b2w_edge_ckpt_finish", "b2w_graph_clear_edge_ckpt",
     "b2w_windex_work_bytes", "b2w_windex_prepare", "b2w_windex_finish", "b2w_graph_clear_windex",
     "b2w_shared_alloc", "b2w_shared_free", "b2w_shared_open", "b2w_shared_close", "b2w_push_rows",
     "b2w_walk_multi", "b2w_alias_build_packed", "b2w_graph_set_alias_packed",
@@ -93,6 +97,11 @@ def lib():
     L.b2w_walk_host.argtypes = [vp, i32, dbl, dbl, i32, vp, vp, u64, u64, u32, u64, vp, u64, C.POINTER(WalkStats), u32]
     L.b2w_walk_multi.argtypes = [i32, C.POINTER(vp), i32, dbl, dbl, i32, C.POINTER(vp), vp, u64, u32, u64, vp, u64,
                                  C.POINTER(WalkStats), u32]
+    L.b2w_edge_ckpt_work_bytes.argtypes = [vp]
+    L.b2w_edge_ckpt_work_bytes.restype = sz
+    L.b2w_edge_ckpt_prepare.argtypes = [vp, vp, vp, sz, C.POINTER(u64), vp]
+    L.b2w_edge_ckpt_finish.argtypes = [vp, dbl, dbl, vp, vp, u64, vp]
+    L.b2w_graph_clear_edge_ckpt.argtypes = [vp]
     L.b2w_windex_work_bytes.argtypes = [vp]
     L.b2w_windex_work_bytes.restype = sz
     L.b2w_windex_prepare.argtypes = [vp, dbl, dbl, i32, vp, vp, vp, vp, vp, sz, C.POINTER(u64), C.POINTER(u64), vp]

@@ -32,6 +32,10 @@ struct b2w_graph {
   const void* edge_rec;
   const uint32_t* edge_tri;
   uint64_t edge_tri_words;
+  // exact-cdf checkpoints of the unweighted SparseOTF replay (borrowed; valid for the p, q they were built with)
+  const float* edge_ckpt;
+  const uint32_t* edge_ckb;
+  double edge_ck_p, edge_ck_q;
   // weighted per-edge index (borrowed; b2w_wedge.cu), valid for the bias parameters it was built with
   const void* w_rec;
   const void* w_exc;

@@ -20,13 +20,15 @@
 // u S (1 - e) the choice is proven; otherwise (~1 % of the steps) the reference's recurrence is replayed exactly from
 // the nearest checkpoint: at most 128 + window sequential additions instead of deg(cur).
 //
-// The first step of a walker has no edge (raw weights) and is evaluated sequentially like the oracle; so is the
-// step after the reference's unchecked choice == deg read (pecanpy.py:559).
+// The first step of a walker has no edge (raw weights): evaluated like the oracle, by its lane on rows of <= 64
+// slots and by the whole warp on longer ones (b2w_offedge.cuh); so is the step after the reference's unchecked
+// choice == deg read (pecanpy.py:559).
 //
 // Reference: pecanpy.py:164-210, :522-561; rw/sparse_rw.py:51-130, :142-295.
 #include <cmath>
 
 #include "b2w_membership.cuh"
+#include "b2w_offedge.cuh"
 #include "b2w_probs.cuh"
 #include "b2w_replay.cuh"
 #include "b2w_rowout.cuh"
@@ -350,6 +352,11 @@ __device__ __noinline__ uint32_t woff_edge(const WalkParams& P, const int extend
   return extend ? otf_choice_seq<true>(P, cur, has_prev, prev, u) : otf_choice_seq<false>(P, cur, has_prev, prev, u);
 }
 
+// first step of a walker on a short row: sequential, one lane (longer rows: the whole warp, b2w_offedge.cuh)
+__device__ __noinline__ uint32_t wfirst_lane(const WalkParams& P, const uint32_t cur, const double u) {
+  return otf_choice_seq<false>(P, cur, false, 0, u);
+}
+
 __device__ __forceinline__ uint32_t wedge_step(const WConsts& C, const uint32_t flags, const WRec& r, const double u,
                                                uint32_t& st_replays) {
   const uint32_t d = r.deg;
@@ -385,44 +392,109 @@ __device__ __forceinline__ uint32_t wedge_step(const WConsts& C, const uint32_t 
   return wreplay(C, r, k_replay, u);
 }
 
-template <int MINB>
+// The lanes of a warp stay converged at loop level, so that the steps without an edge -- the first step of a walker
+// on a long row, the step after the reference's unchecked choice == deg read -- are evaluated by the whole warp.
+constexpr uint32_t FIRST_COOP_DEG = 64;
+
+template <int MINB, bool COOP>
 __global__ void __launch_bounds__(WI_THREADS, MINB) walk_wedge_kernel(const WalkParams P, const WConsts C) {
   __shared__ uint32_t s_stage[8 * WI_THREADS];
   const uint32_t L = P.L;
+  const uint32_t lane = threadIdx.x & 31;
   unsigned long long st_steps = 0;
   uint32_t st_replays = 0, st_overflow = 0;
-  for (uint64_t i = blockIdx.x * (uint64_t)WI_THREADS + threadIdx.x; i < P.n_rows; i += (uint64_t)gridDim.x * WI_THREADS) {
-    RowWriter<WI_THREADS> row;
-    row.begin(P.out + i * P.ld_out, s_stage);
-    uint32_t cur = __ldg(P.start + i), prev = 0;
-    WRec r;
-    r.cs = __ldg(P.indptr + cur);
-    r.deg = __ldg(P.indptr + cur + 1) - r.cs;
-    uint32_t eff = L + 1;
-    bool edge_ok = false;                                             // the first step has no edge
-    row.push(0, cur);
-    uint32_t j = 1;
-    for (; j <= L; ++j) {
-      const uint32_t d = r.deg;
-      if (d == 0) { eff = j; break; }                                 // pecanpy.py:194-196, 204-206
-      const double u = step_uniform(P, i, j);
-      uint32_t choice;
-      if (edge_ok) choice = wedge_step(C, P.flags, r, u, st_replays);
-      else choice = woff_edge(P, C.extend, cur, j > 1, prev, u);      // first step / after an unchecked choice == deg read
-      if (choice == d) ++st_overflow;
-      edge_ok = choice < d;
-      const uint4* rp = reinterpret_cast<const uint4*>(C.rec + (r.cs + choice));   // [cs + d]: next row's first edge (:559)
-      const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-      prev = cur;
-      r.nxt = r0.x; r.kpf = r0.y; r.exc = r0.z; r.deg = r0.w;
-      r.cs = r1.x; r.S = __uint_as_float(r1.y); r.vkp = __uint_as_float(r1.z); r.ckp = r1.w;
-      cur = r.nxt;
-      row.push(j, cur);
+  if (!COOP) {                                                        // plain per-lane loops (the default: 10.1 vs 8.7 G steps/s)
+    for (uint64_t i = blockIdx.x * (uint64_t)WI_THREADS + threadIdx.x; i < P.n_rows; i += (uint64_t)gridDim.x * WI_THREADS) {
+      RowWriter<WI_THREADS> row;
+      row.begin(P.out + i * P.ld_out, s_stage);
+      uint32_t cur = __ldg(P.start + i), prev = 0;
+      WRec r;
+      r.cs = __ldg(P.indptr + cur);
+      r.deg = __ldg(P.indptr + cur + 1) - r.cs;
+      uint32_t eff = L + 1;
+      bool edge_ok = false;                                             // the first step has no edge
+      row.push(0, cur);
+      uint32_t j = 1;
+      for (; j <= L; ++j) {
+        const uint32_t d = r.deg;
+        if (d == 0) { eff = j; break; }                                 // pecanpy.py:194-196, 204-206
+        const double u = step_uniform(P, i, j);
+        uint32_t choice;
+        if (edge_ok) choice = wedge_step(C, P.flags, r, u, st_replays);
+        else choice = woff_edge(P, C.extend, cur, j > 1, prev, u);      // first step / after an unchecked choice == deg read
+        if (choice == d) ++st_overflow;
+        edge_ok = choice < d;
+        const uint4* rp = reinterpret_cast<const uint4*>(C.rec + (r.cs + choice));   // [cs + d]: next row's first edge (:559)
+        const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+        prev = cur;
+        r.nxt = r0.x; r.kpf = r0.y; r.exc = r0.z; r.deg = r0.w;
+        r.cs = r1.x; r.S = __uint_as_float(r1.y); r.vkp = __uint_as_float(r1.z); r.ckp = r1.w;
+        cur = r.nxt;
+        row.push(j, cur);
+      }
+      st_steps += eff - 1;
+      for (uint32_t z = j; z <= L; ++z) row.push(z, 0u);                // zero tail (np.zeros, pecanpy.py:182)
+      row.push(L + 1, eff);
+      row.finish(L + 2);
     }
-    st_steps += eff - 1;
-    for (uint32_t z = j; z <= L; ++z) row.push(z, 0u);                // zero tail (np.zeros, pecanpy.py:182)
-    row.push(L + 1, eff);
-    row.finish(L + 2);
+  }
+  for (uint64_t i = blockIdx.x * (uint64_t)WI_THREADS + threadIdx.x; COOP && __any_sync(B2W_FULL, i < P.n_rows);
+       i += (uint64_t)gridDim.x * WI_THREADS) {
+    const bool alive = i < P.n_rows;
+    RowWriter<WI_THREADS> row;
+    uint32_t cur = 0, prev = 0;
+    WRec r;
+    r.cs = 0; r.deg = 0;
+    if (alive) {
+      row.begin(P.out + i * P.ld_out, s_stage);
+      cur = __ldg(P.start + i);
+      r.cs = __ldg(P.indptr + cur);
+      r.deg = __ldg(P.indptr + cur + 1) - r.cs;
+      row.push(0, cur);
+    }
+    uint32_t eff = L + 1;
+    bool walking = alive;
+    bool edge_ok = false;                                             // the first step has no edge
+    for (uint32_t j = 1; j <= L; ++j) {
+      const uint32_t d = r.deg;
+      if (walking && d == 0) { eff = j; walking = false; }            // pecanpy.py:194-196, 204-206
+      uint32_t choice = 0;
+      double u = 0.0;
+      bool coop = false;
+      if (walking) {
+        u = step_uniform(P, i, j);
+        if (edge_ok) choice = wedge_step(C, P.flags, r, u, st_replays);
+        else if (j == 1 && d <= FIRST_COOP_DEG) choice = wfirst_lane(P, cur, u);
+        else coop = true;
+      }
+      __syncwarp();
+      uint32_t off = __ballot_sync(B2W_FULL, coop);
+      while (off) {
+        const int src = __ffs(off) - 1;
+        off &= off - 1;
+        const uint32_t bcur = __shfl_sync(B2W_FULL, cur, src), bprev = __shfl_sync(B2W_FULL, prev, src);
+        const double bu = __shfl_sync(B2W_FULL, u, src);
+        const bool bhp = j > 1;
+        const uint32_t c = C.extend ? offedge_w_warp<true>(P, bcur, bhp, bprev, bu) : offedge_w_warp<false>(P, bcur, bhp, bprev, bu);
+        if (lane == (uint32_t)src) choice = c;
+      }
+      if (walking) {
+        if (choice == d) ++st_overflow;
+        edge_ok = choice < d;
+        const uint4* rp = reinterpret_cast<const uint4*>(C.rec + (r.cs + choice));   // [cs + d]: next row's first edge (:559)
+        const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+        prev = cur;
+        r.nxt = r0.x; r.kpf = r0.y; r.exc = r0.z; r.deg = r0.w;
+        r.cs = r1.x; r.S = __uint_as_float(r1.y); r.vkp = __uint_as_float(r1.z); r.ckp = r1.w;
+        cur = r.nxt;
+      }
+      if (alive) row.push(j, walking ? cur : 0u);                     // zero tail after a dead end (np.zeros, pecanpy.py:182)
+    }
+    if (alive) {
+      st_steps += eff - 1;
+      row.push(L + 1, eff);
+      row.finish(L + 2);
+    }
   }
   if (P.stats && !(P.flags & B2W_FLAG_NO_FILTER_STATS)) {
     for (int o = 16; o; o >>= 1) {
@@ -560,8 +632,10 @@ int b2w_launch_wedge(const b2w_graph* g, const WalkParams& P, cudaStream_t s) {
   unsigned blocks = (unsigned)(want < cap ? want : cap);
   if (blocks < 1) blocks = 1;
   const int mb = (int)((P.flags >> 16) & 0xF);                        // tuning: resident CTAs per SM (0 = default)
-  if (mb == 5) walk_wedge_kernel<5><<<blocks, WI_THREADS, 0, s>>>(P, C);
-  else if (mb == 3) walk_wedge_kernel<3><<<blocks, WI_THREADS, 0, s>>>(P, C);
-  else walk_wedge_kernel<4><<<blocks, WI_THREADS, 0, s>>>(P, C);
+  const bool coop = (P.flags & B2W_FLAG_OFFEDGE_WARP) != 0;          // opt-in: measured slower here (plain loops are the default)
+  if (coop) walk_wedge_kernel<4, true><<<blocks, WI_THREADS, 0, s>>>(P, C);
+  else if (mb == 5) walk_wedge_kernel<5, false><<<blocks, WI_THREADS, 0, s>>>(P, C);
+  else if (mb == 3) walk_wedge_kernel<3, false><<<blocks, WI_THREADS, 0, s>>>(P, C);
+  else walk_wedge_kernel<4, false><<<blocks, WI_THREADS, 0, s>>>(P, C);
   return b2w_cuda_fail(cudaGetLastError(), "walk_wedge_kernel launch");
 }

@@ -66,6 +66,9 @@ class WalkEngine:
         self._edge_index_failed = False
         self.windex_ms: Optional[float] = None
         self._windex_key = None
+        self.edge_ckpt_ms: Optional[float] = None
+        self.edge_ckpt_floats = 0
+        self._edge_ckpt_key = None
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -184,6 +187,48 @@ class WalkEngine:
         self.edge_index_words = int(words.value)
         return True
 
+    def build_edge_ckpt(self, p: float, q: float) -> bool:
+        """Checkpoints of the exact cdf for the replays of the unweighted edge-index kernel (b2w_edge_ckpt_*), for
+        these p, q.  Returns False when they do not fit (the kernel then replays from the start of the row)."""
+        if not self.has_edge_index:
+            return False
+        key = (float(p), float(q))
+        if self._edge_ckpt_key == key:
+            return True
+        self.drop_edge_ckpt()
+        gi = self.info()
+        with torch.cuda.device(self.device):
+            free, _ = torch.cuda.mem_get_info(self.device)
+            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            t0.record()
+            wb = int(self.lib.b2w_edge_ckpt_work_bytes(self.handle))
+            work = torch.empty(wb, dtype=torch.uint8, device=self.device)
+            ckb = torch.empty(gi.num_nodes + 1, dtype=torch.int32, device=self.device)
+            n_ck = C.c_uint64(0)
+            rc = self.lib.b2w_edge_ckpt_prepare(self.handle, _ptr(ckb), _ptr(work), wb, C.byref(n_ck), C.c_void_p(stream))
+            if rc == capi.ERR_UNSUPPORTED or (rc == capi.OK and 4 * n_ck.value > 0.4 * free):
+                self._edge_ckpt_key = None
+                return False
+            capi.check(rc, "b2w_edge_ckpt_prepare")
+            ck = torch.empty(max(int(n_ck.value), 1), dtype=torch.float32, device=self.device)
+            capi.check(self.lib.b2w_edge_ckpt_finish(self.handle, float(p), float(q), _ptr(ckb), _ptr(ck), int(n_ck.value),
+                                                     C.c_void_p(stream)), "b2w_edge_ckpt_finish")
+            t1.record()
+            t1.synchronize()
+            self.edge_ckpt_ms = t0.elapsed_time(t1)
+        self._keep["edge_ckb"], self._keep["edge_ckpt"] = ckb, ck
+        self._edge_ckpt_key = key
+        self.edge_ckpt_floats = int(n_ck.value)
+        return True
+
+    def drop_edge_ckpt(self):
+        if self.kind == "csr" and self.handle:
+            capi.check(self.lib.b2w_graph_clear_edge_ckpt(self.handle), "b2w_graph_clear_edge_ckpt")
+        self._keep.pop("edge_ckb", None)
+        self._keep.pop("edge_ckpt", None)
+        self._edge_ckpt_key = None
+
     def build_windex(self, p: float, q: float, extend: bool = False) -> bool:
         """Build the WEIGHTED per-edge index for these bias parameters (b2w_windex_prepare / _finish) and attach it:
         SparseOTF on weighted graphs, node2vec+ and arbitrary p, q then run the lane-per-walker kernel of
@@ -239,6 +284,7 @@ class WalkEngine:
         self._windex_key = None
 
     def drop_edge_index(self):
+        self.drop_edge_ckpt()
         if self.kind == "csr" and self.handle:
             capi.check(self.lib.b2w_graph_set_edge_index(self.handle, None, None, 0), "b2w_graph_set_edge_index")
         self._keep.pop("edge_rec", None)
@@ -254,7 +300,11 @@ class WalkEngine:
         if mode == capi.MODE_SPARSE_OTF:
             name = self.lib.b2w_walk_kernel_name(self.handle, mode, float(p), float(q), int(bool(extend)), int(flags)).decode()
             if name == "walk_uw_kernel" and not self.has_edge_index:
-                self.build_edge_index()
+                if self.build_edge_index():
+                    name = "walk_uw_edge_kernel"
+            if name == "walk_uw_edge_kernel":
+                if not (flags & capi.FLAG_NO_CKPT) and self._edge_ckpt_key != (float(p), float(q)):
+                    self.build_edge_ckpt(p, q)
             elif name == "walk_sparse_warp_kernel" and not (flags & (capi.FLAG_NO_UNWEIGHTED_KERNEL | capi.FLAG_COOP | 0xFF00)):
                 # weighted graph / node2vec+ / biases off the exact grid: the weighted index for THESE parameters
                 if not extend or self.thr is not None:

@@ -79,7 +79,8 @@ def test_edge_index_content(name):
 
 
 @pytest.mark.parametrize("pq", [(4.0, 0.25), (0.5, 2.0), (1.0, 1.0), (0.25, 4.0), (2.0, 0.5)])
-@pytest.mark.parametrize("flags", [0, 1], ids=["filter", "forced-replay"])
+@pytest.mark.parametrize("flags", [0, 1, 0x80, 0x81, 0x2000000, 0x2000001],
+                         ids=["filter", "forced-replay", "filter-no-ckpt", "forced-replay-no-ckpt", "lane-loops", "lane-loops-replay"])
 def test_edge_kernel_equals_oracle_and_membership_kernel(pq, flags):
     """Hub rows above 1024 neighbours, many common neighbours per edge (dense core), both filter and replay."""
     import torch
@@ -92,8 +93,10 @@ def test_edge_kernel_equals_oracle_and_membership_kernel(pq, flags):
     eng = WalkEngine.from_csr(indptr, indices, data)
     got = eng.walk("SparseOTF", p, q, start, 40, seed=77, flags=flags)
     assert eng.kernel_name("SparseOTF", p, q) == "walk_uw_edge_kernel"
+    assert (eng.edge_ckpt_floats > 0) == (not flags & 0x80)           # checkpoints are built on demand, per (p, q)
     st = eng.stats()
-    ref = eng.walk("SparseOTF", p, q, start, 40, seed=77, flags=flags | 0x40)
+    assert int((indptr[1:] - indptr[:-1]).max()) > 256               # default here: converged warps (long rows)
+    ref = eng.walk("SparseOTF", p, q, start, 40, seed=77, flags=(flags & 1) | 0x40)
     assert eng.kernel_name("SparseOTF", p, q, flags=0x40) == "walk_uw_kernel"
     assert torch.equal(got, ref)
     st2 = eng.stats()                                                 # (the replay counts differ by design)
@@ -137,9 +140,48 @@ def test_edge_kernel_after_overflow_read():
     feed[rng.random((rows, L)) < 0.08] = 1.0 - 2.0 ** -53             # the largest double below 1
     eng = WalkEngine.from_csr(indptr, indices, data)
     for p, q in ((4.0, 0.25), (0.5, 2.0)):
-        got = eng.walk("SparseOTF", p, q, start, L, rng=capi.RNG_FEED, feed=feed.ravel()).cpu().numpy().view(np.uint32)
-        assert eng.kernel_name("SparseOTF", p, q) == "walk_uw_edge_kernel"
-        assert eng.stats()["overflow_choices"] > 0
         want = orc.walk_csr("SparseOTF", indptr, indices, data, p, q, start, L, rng=orc.RNG_FEED, feed=feed)
-        assert np.array_equal(got, want)
+        # the step without an edge: by the walker's lane (plain loops) and by its whole warp (converged loops)
+        for flags in (0, capi.FLAG_OFFEDGE_LANE, capi.FLAG_OFFEDGE_WARP):
+            got = eng.walk("SparseOTF", p, q, start, L, rng=capi.RNG_FEED, feed=feed.ravel(), flags=flags).cpu().numpy().view(np.uint32)
+            assert eng.kernel_name("SparseOTF", p, q) == "walk_uw_edge_kernel"
+            assert eng.stats()["overflow_choices"] > 0
+            assert np.array_equal(got, want), flags
+    eng.close()
+
+
+def test_edge_checkpoints_equal_the_reference_cdf():
+    """The checkpoints are the reference's own float32 cdf (sequential cumsum of w / w.sum(), rw/sparse_rw.py:89,
+    pecanpy.py:556) after elements 127, 255, ... of row(cur), for every stored edge into a row of >= 128 slots."""
+    from oracle import oracle as orc
+    from pecanpy_b200.engine import WalkEngine
+    from pecanpy_b200.synth import power_law_csr
+    indptr, indices, data = power_law_csr(3000, 60000, seed=11)
+    eng = WalkEngine.from_csr(indptr, indices, data)
+    p, q = 4.0, 0.25
+    assert eng.build_edge_index() and eng.build_edge_ckpt(p, q)
+    ckb = eng._keep["edge_ckb"].cpu().numpy().view(np.uint32)
+    ck = eng._keep["edge_ckpt"].cpu().numpy()
+    ip = indptr.astype(np.int64)
+    deg = ip[1:] - ip[:-1]
+    checked = 0
+    for cur in np.argsort(-deg)[:12]:
+        d = int(deg[cur])
+        if d < 128:
+            continue
+        nck = d // 128
+        row = indices[ip[cur]:ip[cur + 1]]
+        for kp in (0, d // 3, d - 1):
+            prev = int(row[kp])
+            probs = orc.sparse_probs(indptr, indices, data, p, q, int(cur), prev)
+            cdf = np.float32(0)
+            want = []
+            for k in range(nck * 128):
+                cdf = np.float32(cdf + probs[k])
+                if k % 128 == 127:
+                    want.append(cdf)
+            got = ck[int(ckb[cur]) + kp * nck: int(ckb[cur]) + (kp + 1) * nck]
+            assert np.array_equal(got.view(np.uint32), np.array(want, np.float32).view(np.uint32)), (cur, kp)
+            checked += 1
+    assert checked >= 6
     eng.close()

@@ -128,7 +128,7 @@ CASES = [(0.5, 2.0, False), (4.0, 0.25, False), (0.3, 0.7, False), (1.0, 1.0, Fa
 
 
 @pytest.mark.parametrize("p,q,extend", CASES)
-@pytest.mark.parametrize("flags", [0, 1], ids=["filter", "forced-replay"])
+@pytest.mark.parametrize("flags", [0, 1, 0x1000000], ids=["filter", "forced-replay", "warp-loops"])
 def test_wedge_kernel_equals_oracle_and_streaming_kernel(p, q, extend, flags):
     """Weighted power-law graph with hub rows above 1024 slots (checkpointed replays, multi-exception edges)."""
     import torch
@@ -142,7 +142,7 @@ def test_wedge_kernel_equals_oracle_and_streaming_kernel(p, q, extend, flags):
     got = eng.walk("SparseOTF", p, q, start, 40, seed=31, extend=extend, flags=flags)
     assert eng.kernel_name("SparseOTF", p, q, extend) == "walk_wedge_kernel"
     st = eng.stats()
-    ref = eng.walk("SparseOTF", p, q, start, 40, seed=31, extend=extend, flags=flags | 0x40)
+    ref = eng.walk("SparseOTF", p, q, start, 40, seed=31, extend=extend, flags=(flags & 1) | 0x40)
     assert eng.kernel_name("SparseOTF", p, q, extend, flags=0x40) == "walk_sparse_warp_kernel"
     assert torch.equal(got, ref)
     st2 = eng.stats()
@@ -182,10 +182,11 @@ def test_wedge_kernel_after_overflow_read_and_dead_ends():
     feed = rng.random((rows, L))
     feed[rng.random((rows, L)) < 0.08] = 1.0 - 2.0 ** -53             # the largest double below 1
     eng = WalkEngine.from_csr(indptr, indices, data)
-    got = eng.walk("SparseOTF", 0.5, 2.0, start, L, rng=capi.RNG_FEED, feed=feed.ravel()).cpu().numpy().view(np.uint32)
-    assert eng.kernel_name("SparseOTF", 0.5, 2.0) == "walk_wedge_kernel" and eng.stats()["overflow_choices"] > 0
     want = orc.walk_csr("SparseOTF", indptr, indices, data, 0.5, 2.0, start, L, rng=orc.RNG_FEED, feed=feed)
-    assert np.array_equal(got, want)
+    for flags in (0, capi.FLAG_OFFEDGE_WARP):                        # steps without an edge: by the lane / by the warp
+        got = eng.walk("SparseOTF", 0.5, 2.0, start, L, rng=capi.RNG_FEED, feed=feed.ravel(), flags=flags).cpu().numpy().view(np.uint32)
+        assert eng.kernel_name("SparseOTF", 0.5, 2.0) == "walk_wedge_kernel" and eng.stats()["overflow_choices"] > 0
+        assert np.array_equal(got, want), flags
     eng.close()
     c = load("dir150_sparseotf_deadends")
     start = orc.shuffled_start(c["indptr"].size - 1, 20, 1)
