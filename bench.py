@@ -459,6 +459,8 @@ def run_workload(name, args, K, W, rank, world, local_rank, *, do_e2e=True, do_c
             rec = json.load(open(tpath)).get(name, {})
             if rec.get("kernel", kname) == kname:
                 traffic = rec.get("dram_bytes_per_launch")
+                if traffic and rec.get("num_walks"):        # captured with fewer walks per node than this launch
+                    traffic = int(traffic * wl["num_walks"] / rec["num_walks"])
                 note = rec.get("note")
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic, "kernel": kname, "kernel_ms": 1e3 * kernel_s,

@@ -73,6 +73,7 @@ typedef enum {
 #define B2W_FLAG_NO_CKPT 0x80u /* unweighted SparseOTF through the edge index: replay from the start of the row, not from a checkpoint */
 #define B2W_FLAG_OFFEDGE_WARP 0x1000000u /* edge-index kernels: converged warps, steps without an edge by the whole warp (default on graphs with rows > 256) */
 #define B2W_FLAG_OFFEDGE_LANE 0x2000000u /* edge-index kernels: plain per-lane loops, steps without an edge by their own lane */
+#define B2W_FLAG_L2_PERSIST 0x4000000u /* PreComp through the edge index: pin the edge records in L2 (access-policy window) */
 #define B2W_FLAG_GROUP(n) (((uint32_t)(n) & 0xFFu) << 8) /* tuning: lanes per walker (8/16/32), 0 = auto */
 
 typedef struct b2w_graph b2w_graph; /* opaque */
@@ -243,11 +244,11 @@ int b2w_graph_clear_edge_ckpt(b2w_graph* g);
  * O(log deg) arithmetic for one lane: per row the BASE biased weights (slot neither prev nor common) and their f64
  * prefix sums; per edge a 32-byte record (next node, degree, row start, position and weight of the return edge, the
  * reference's exact f32 normaliser of that step), the common neighbours whose weight deviates from the base
- * ("exceptions": position, exact f32 weight, f64 prefix of the deviations) and, for rows of >= 128 slots, checkpoints
- * of the reference's exact f32 cdf every 128 positions (so that the rare exact replay is bounded).  Walks are
+ * ("exceptions": position, exact f32 weight, f64 prefix of the deviations) and, for rows of >= 32 slots, checkpoints
+ * of the reference's exact f32 cdf every 32 positions (so that the rare exact replay is bounded).  Walks are
  * bit-identical with and without it.  Caller-owned arrays:
  *     d_rec   32 bytes x (nnz + 1), 32-byte aligned        d_bw  float[nnz]        d_bq  double[nnz]
- *     d_exc   24 bytes x exc_entries                       d_ckpt float[ckpt_floats]
+ *     d_ckb   uint32[n + 1] (per-node checkpoint offsets)  d_exc 24 bytes x exc_entries    d_ckpt float[ckpt_floats]
  * b2w_windex_prepare fills d_rec / d_bw / d_bq and reports the two data-dependent sizes (synchronous;
  * B2W_ERR_UNSUPPORTED when they do not fit 32-bit offsets); b2w_windex_finish fills d_exc / d_ckpt, computes the
  * normalisers and attaches the index (borrowed until b2w_graph_clear_windex / destroy; synchronous).  d_work: at least
@@ -255,11 +256,11 @@ int b2w_graph_clear_edge_ckpt(b2w_graph* g);
  * extend and the d_thr pointer are the ones it was built with (B2W_FLAG_NO_EDGE_INDEX: never). */
 size_t b2w_windex_work_bytes(const b2w_graph* g);
 int b2w_windex_prepare(const b2w_graph* g, double p, double q, int extend, const float* d_thr, void* d_rec, float* d_bw,
-                       double* d_bq, void* d_work, size_t work_bytes, uint64_t* h_exc_entries, uint64_t* h_ckpt_floats,
-                       void* stream);
+                       double* d_bq, uint32_t* d_ckb, void* d_work, size_t work_bytes, uint64_t* h_exc_entries,
+                       uint64_t* h_ckpt_floats, void* stream);
 int b2w_windex_finish(b2w_graph* g, double p, double q, int extend, const float* d_thr, void* d_rec, float* d_bw,
-                      double* d_bq, void* d_exc, uint64_t exc_entries, float* d_ckpt, uint64_t ckpt_floats, void* d_work,
-                      size_t work_bytes, void* stream);
+                      double* d_bq, const uint32_t* d_ckb, void* d_exc, uint64_t exc_entries, float* d_ckpt,
+                      uint64_t ckpt_floats, void* d_work, size_t work_bytes, void* stream);
 int b2w_graph_clear_windex(b2w_graph* g);
 
 /* ---- the walk kernel -------------------------------------------------------------------

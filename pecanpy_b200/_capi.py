@@ -104,8 +104,8 @@ def lib():
     L.b2w_graph_clear_edge_ckpt.argtypes = [vp]
     L.b2w_windex_work_bytes.argtypes = [vp]
     L.b2w_windex_work_bytes.restype = sz
-    L.b2w_windex_prepare.argtypes = [vp, dbl, dbl, i32, vp, vp, vp, vp, vp, sz, C.POINTER(u64), C.POINTER(u64), vp]
-    L.b2w_windex_finish.argtypes = [vp, dbl, dbl, i32, vp, vp, vp, vp, vp, u64, vp, u64, vp, sz, vp]
+    L.b2w_windex_prepare.argtypes = [vp, dbl, dbl, i32, vp, vp, vp, vp, vp, vp, sz, C.POINTER(u64), C.POINTER(u64), vp]
+    L.b2w_windex_finish.argtypes = [vp, dbl, dbl, i32, vp, vp, vp, vp, vp, vp, u64, vp, u64, vp, sz, vp]
     L.b2w_graph_clear_windex.argtypes = [vp]
     L.b2w_shared_alloc.argtypes = [i32, sz, C.POINTER(vp), C.c_char_p]
     L.b2w_shared_free.argtypes = [i32, vp]

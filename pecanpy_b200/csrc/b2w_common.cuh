@@ -42,6 +42,7 @@ struct b2w_graph {
   const float* w_bw;
   const double* w_bq;
   const float* w_ckpt;
+  const uint32_t* w_ckb;
   const float* w_thr;
   double w_p, w_q;
   int w_extend;

@@ -12,13 +12,14 @@
 //     w/p, the reference's exact f32 normaliser S of that (prev, cur) pair, and offsets of the two lists below;
 //   * per edge, the EXCEPTIONS: the common neighbours whose biased weight differs from the base (node2vec: w;
 //     node2vec+: w or w * alpha(t)), with position, exact f32 value, and the f64 prefix of the deviations;
-//   * per edge with deg(cur) >= 128, CHECKPOINTS of the reference's exact f32 cdf every 128 positions.
+//   * per edge into a row of >= 32 slots (whose return edge exists), CHECKPOINTS of the reference's exact f32 cdf
+//     every 32 positions, laid out [node][slot of prev][j].
 // A step then is: un-normalised prefix P(k) = bq[k] + deviations up to k (+ the return-edge deviation), the
 // reference's cdf_k = (P(k) / S)(1 + t), |t| <= e_k = 1.02 (k + 3) 2^-24 + f64 slack (S is the reference's own f32
 // sum, so only the divisions and the cumsum round), and the first k with P(k) >= u S (1 + e) found by a bisection
 // over the exception list and a bisection over bq inside one segment.  If the element before it is provably below
 // u S (1 - e) the choice is proven; otherwise (~1 % of the steps) the reference's recurrence is replayed exactly from
-// the nearest checkpoint: at most 128 + window sequential additions instead of deg(cur).
+// the nearest checkpoint: at most 32 + window sequential additions instead of deg(cur).
 //
 // The first step of a walker has no edge (raw weights): evaluated like the oracle, by its lane on rows of <= 64
 // slots and by the whole warp on longer ones (b2w_offedge.cuh); so is the step after the reference's unchecked
@@ -41,14 +42,14 @@ constexpr uint32_t KPF_POS_MASK = 0x3FFFFFFFu;
 constexpr uint32_t KPF_NOTFOUND = 0x40000000u;
 constexpr uint32_t KPF_HAS_EXC = 0x80000000u;
 constexpr int WI_THREADS = 256;
-constexpr uint32_t CKP = 128;                                         // checkpoint spacing (positions)
+constexpr uint32_t CKP = 32;                                          // checkpoint spacing (positions)
 
 struct __align__(16) WRec {
   uint32_t nxt, kpf, exc, deg;       // exc: offset of the exception list (entries); in the count pass: its length
   uint32_t cs;                       // indptr[nxt]
   float S;                           // the reference's sequential f32 sum of the biased weights of row(nxt) given prev
   float vkp;                         // biased weight of the return edge, f32(w / p)
-  uint32_t ckp;                      // offset of the checkpoints (floats); in the count pass: their number
+  float bkp;                         // base weight of the same slot (what vkp replaces)
 };
 static_assert(sizeof(WRec) == 32, "record size");
 
@@ -134,7 +135,7 @@ __global__ void __launch_bounds__(WI_THREADS) wedge_kernel(const WalkParams P, c
     }
     uint32_t work = __ballot_sync(B2W_FULL, FILL ? (real && (kpf & KPF_HAS_EXC)) : (real && bd > 0));
     uint32_t my_cnt = 0, my_kpf = KPF_NOTFOUND;
-    float my_vkp = 0.f;
+    float my_vkp = 0.f, my_bkp = 0.f;
     while (work) {
       const int t = __ffs(work) - 1;
       work &= work - 1;
@@ -151,7 +152,10 @@ __global__ void __launch_bounds__(WI_THREADS) wedge_kernel(const WalkParams P, c
         const uint32_t pos = lower_bound_eq<true>(brow, tbd, ta, kb, found);
         if (lane == (uint32_t)t) {
           my_kpf = pos | (found ? 0u : KPF_NOTFOUND);
-          if (found) my_vkp = div_by(__ldg(P.data + tbs + pos), P.p, P.invp_f, P.p_pow2);   // rw/sparse_rw.py:87 / :126
+          if (found) {
+            my_vkp = div_by(__ldg(P.data + tbs + pos), P.p, P.invp_f, P.p_pow2);   // rw/sparse_rw.py:87 / :126
+            my_bkp = __ldg(bw + tbs + pos);
+          }
         }
       }
       const uint32_t fwd_cost = ((tbd + 31) >> 5) * (ka + 3);
@@ -214,7 +218,7 @@ __global__ void __launch_bounds__(WI_THREADS) wedge_kernel(const WalkParams P, c
       if (my_cnt) my_kpf |= KPF_HAS_EXC;
       WRec r;
       r.nxt = b; r.kpf = my_kpf; r.exc = my_cnt ? my_cnt + 1 : 0u; r.deg = bd; r.cs = bs;
-      r.S = 0.f; r.vkp = my_vkp; r.ckp = real ? bd / CKP : 0u;
+      r.S = 0.f; r.vkp = my_vkp; r.bkp = my_bkp;
       rec[e] = r;
     }
   }
@@ -246,7 +250,7 @@ struct EdgeRow {
 // ---- pass 4: per edge, the reference's exact normaliser and cdf checkpoints (one lane per edge, sequential)
 __global__ void __launch_bounds__(WI_THREADS) wsum_kernel(const uint64_t nnz, WRec* __restrict__ rec,
                                                           const float* __restrict__ bw, const WExc* __restrict__ exc,
-                                                          float* __restrict__ ckpt) {
+                                                          const uint32_t* __restrict__ ckb, float* __restrict__ ckpt) {
   for (uint64_t e = blockIdx.x * (uint64_t)WI_THREADS + threadIdx.x; e < nnz; e += (uint64_t)gridDim.x * WI_THREADS) {
     const WRec r = rec[e];
     if (r.deg == 0) continue;
@@ -261,10 +265,10 @@ __global__ void __launch_bounds__(WI_THREADS) wsum_kernel(const uint64_t nnz, WR
     for (uint32_t k = 0; k < r.deg; ++k) S = __fadd_rn(S, row.weight(k));   // sequential f32 sum (arraymath.py:161-174)
     rec[e].S = S;
     const uint32_t nck = r.deg / CKP;
-    if (nck) {
+    if (nck && row.kp != NONE) {                                      // checkpoints live at [node][slot of prev][j]
       row.seek(0);
       float cdf = 0.f;
-      float* const out = ckpt + r.ckp;
+      float* const out = ckpt + ((size_t)ckb[r.nxt] + (size_t)row.kp * nck);
       const uint32_t last = nck * CKP;
       for (uint32_t k = 0; k < last; ++k) {
         cdf = __fadd_rn(cdf, __fdiv_rn(row.weight(k), S));            // probs = w / S; sequential f32 cumsum
@@ -281,6 +285,7 @@ struct WConsts {
   const float* __restrict__ bw;
   const double* __restrict__ bq;
   const float* __restrict__ ckpt;
+  const uint32_t* __restrict__ ckb;  // per node: offset of its checkpoint block
   double slack;                      // relative slack for the f64 evaluation of P(k)
   int extend;
 };
@@ -290,6 +295,7 @@ struct WStep {
   const WExc* __restrict__ lst;
   uint32_t m, kp, d;
   double dk;                         // deviation of the return edge: vkp - b[kp]
+  double inv_slope;                  // d / S: slots per unit of un-normalised weight, on average
 
   // un-normalised prefix at an exception / inside a segment
   __device__ __forceinline__ double at_exc(const uint32_t i) const {
@@ -310,7 +316,37 @@ struct WStep {
     const double Dseg = i ? __ldg(&lst[i - 1].D) : 0.0;
     const uint32_t klo = i ? __ldg(&lst[i - 1].pos) + 1 : 0u;
     const uint32_t khi = i < m ? __ldg(&lst[i].pos) : d;              // the segment is [klo, khi)
+    // first k in [klo, khi) with P(k) >= T.  Invariant: P(k) < T for every k < a;  P(b) >= T or b == khi.
     uint32_t a = klo, b = khi;
+    if (b - a > 16u) {
+      // The prefix grows by about S / d per slot: two interpolation probes land next to the answer, a gallop from
+      // there closes the bracket within a cache line or two -- a plain bisection of a long row touches a new 64-byte
+      // line of the f64 prefix array at all but its last three probes (444 DRAM bytes per step on BASELINE #3).
+      const double Pa = i ? at_exc(i - 1) : 0.0;                      // P(klo - 1)
+      double est = (double)a + (T - Pa) * inv_slope;
+      uint32_t g = est <= (double)a ? a : (est >= (double)(b - 1) ? b - 1 : (uint32_t)est);
+      double Pg = in_seg(g, Dseg);
+      bool ge = Pg >= T;
+      if (ge) b = g; else a = g + 1;
+      if (a < b) {
+        est = (double)g + (T - Pg) * inv_slope;
+        const uint32_t g2 = est <= (double)a ? a : (est >= (double)(b - 1) ? b - 1 : (uint32_t)est);
+        Pg = in_seg(g2, Dseg);
+        ge = Pg >= T;
+        if (ge) b = g2; else a = g2 + 1;
+        if (ge) {                                                     // gallop towards smaller k from b
+          for (uint32_t step = 1; a < b; step <<= 1) {
+            const uint32_t c = (b - a > step) ? b - step : a;
+            if (in_seg(c, Dseg) >= T) b = c; else { a = c + 1; break; }
+          }
+        } else {                                                      // gallop towards larger k from a
+          for (uint32_t step = 1; a < b; step <<= 1) {
+            const uint32_t c = (b - a > step) ? a + step - 1 : b - 1;
+            if (in_seg(c, Dseg) >= T) { b = c; break; } else a = c + 1;
+          }
+        }
+      }
+    }
     while (a < b) {
       const uint32_t mid = (a + b) >> 1;
       if (in_seg(mid, Dseg) >= T) b = mid; else a = mid + 1;
@@ -334,9 +370,9 @@ __device__ __noinline__ uint32_t wreplay(const WConsts& C, const WRec& r, const 
   row.kp = (r.kpf & KPF_NOTFOUND) ? NONE : (r.kpf & KPF_POS_MASK);
   row.vkp = r.vkp;
   const uint32_t nck = r.deg / CKP;
-  uint32_t j = k0 / CKP;
+  uint32_t j = row.kp != NONE ? k0 / CKP : 0u;                        // (no return edge: no checkpoints for this edge)
   if (j > nck) j = nck;
-  float cdf = j ? __ldg(C.ckpt + r.ckp + j - 1) : 0.f;                // cdf after element j * CKP - 1
+  float cdf = j ? __ldg(C.ckpt + ((size_t)__ldg(C.ckb + r.nxt) + (size_t)row.kp * nck + (j - 1))) : 0.f;   // after element j CKP - 1
   const uint32_t s = j * CKP;
   row.seek(s);
   const float ub = upper_float(u);                                    // cdf < u  <=>  cdf < ub
@@ -366,23 +402,27 @@ __device__ __forceinline__ uint32_t wedge_step(const WConsts& C, const uint32_t 
   W.m = 0; W.lst = C.exc;
   if (r.kpf & KPF_HAS_EXC) { W.m = __ldg(&C.exc[r.exc].pos); W.lst = C.exc + r.exc + 1; }
   W.kp = (r.kpf & KPF_NOTFOUND) ? NONE : (r.kpf & KPF_POS_MASK);
-  W.dk = W.kp != NONE ? __dsub_rn((double)r.vkp, (double)__ldg(C.bw + r.cs + W.kp)) : 0.0;
+  W.dk = W.kp != NONE ? __dsub_rn((double)r.vkp, (double)r.bkp) : 0.0;
   const double S = (double)r.S;
+  W.inv_slope = (double)d / S;
   const bool sane = r.S > 0.f && r.S < 3.0e38f && d <= 160000u;       // (a zero / overflowing sum: replay, like the reference)
   uint32_t k_replay = 0;
-  if (sane && !(flags & B2W_FLAG_FORCE_EXACT_REPLAY)) {
+  if (sane) {
+    const bool forced = (flags & B2W_FLAG_FORCE_EXACT_REPLAY) != 0;   // test hook: replay (from a checkpoint) every step
     const double EC = 1.02 * 5.9604644775390625e-08;                  // 1.02 * 2^-24
     const double uS = u * S;
     const double e_row = EC * (double)(d + 2) + C.slack;
     double Pk, Pprev;
-    // upper bound k1 of the answer from the most conservative "sure" threshold, thresholds at that position
-    const uint32_t k1 = W.first_at_least(uS * (1.0 + e_row + 2.0 * e_row * e_row), Pk, Pprev);
-    if (k1 < d) {
-      const double e = EC * (double)(k1 + 3) + C.slack;
-      const double t_poss = uS * (1.0 - e), t_sure = uS * (1.0 + e + 2.0 * e * e);
-      if (Pprev < t_poss) return k1;                                  // P(k1) >= t_hi >= t_sure: proven
-      const uint32_t k2 = W.first_at_least(t_sure, Pk, Pprev);        // k2 <= k1, same e is valid
-      if (k2 < d && Pprev < t_poss) return k2;
+    if (!forced) {
+      // upper bound k1 of the answer from the most conservative "sure" threshold, thresholds at that position
+      const uint32_t k1 = W.first_at_least(uS * (1.0 + e_row + 2.0 * e_row * e_row), Pk, Pprev);
+      if (k1 < d) {
+        const double e = EC * (double)(k1 + 3) + C.slack;
+        const double t_poss = uS * (1.0 - e), t_sure = uS * (1.0 + e + 2.0 * e * e);
+        if (Pprev < t_poss && Pk >= t_sure) return k1;                // (P(k1) >= t_hi >= t_sure) proven
+        const uint32_t k2 = W.first_at_least(t_sure, Pk, Pprev);      // k2 <= k1, same e is valid
+        if (k2 < d && Pprev < t_poss && Pk >= t_sure) return k2;
+      }
     }
     // ambiguous: the answer is at or after the first k with P(k) >= u S (1 - e_row)
     k_replay = W.first_at_least(uS * (1.0 - e_row), Pk, Pprev);
@@ -428,7 +468,7 @@ __global__ void __launch_bounds__(WI_THREADS, MINB) walk_wedge_kernel(const Walk
         const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
         prev = cur;
         r.nxt = r0.x; r.kpf = r0.y; r.exc = r0.z; r.deg = r0.w;
-        r.cs = r1.x; r.S = __uint_as_float(r1.y); r.vkp = __uint_as_float(r1.z); r.ckp = r1.w;
+        r.cs = r1.x; r.S = __uint_as_float(r1.y); r.vkp = __uint_as_float(r1.z); r.bkp = __uint_as_float(r1.w);
         cur = r.nxt;
         row.push(j, cur);
       }
@@ -485,7 +525,7 @@ __global__ void __launch_bounds__(WI_THREADS, MINB) walk_wedge_kernel(const Walk
         const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
         prev = cur;
         r.nxt = r0.x; r.kpf = r0.y; r.exc = r0.z; r.deg = r0.w;
-        r.cs = r1.x; r.S = __uint_as_float(r1.y); r.vkp = __uint_as_float(r1.z); r.ckp = r1.w;
+        r.cs = r1.x; r.S = __uint_as_float(r1.y); r.vkp = __uint_as_float(r1.z); r.bkp = __uint_as_float(r1.w);
         cur = r.nxt;
       }
       if (alive) row.push(j, walking ? cur : 0u);                     // zero tail after a dead end (np.zeros, pecanpy.py:182)
@@ -510,6 +550,21 @@ __global__ void __launch_bounds__(WI_THREADS, MINB) walk_wedge_kernel(const Walk
   }
 }
 
+// per node: floats of its checkpoint block = deg * (deg / CKP), to be prefix-summed
+__global__ void __launch_bounds__(WI_THREADS) wckpt_count_kernel(const uint32_t n, const uint32_t* __restrict__ indptr,
+                                                                 uint32_t* __restrict__ ckb, unsigned int* __restrict__ too_big) {
+  for (uint64_t v = blockIdx.x * (uint64_t)WI_THREADS + threadIdx.x; v <= n; v += (uint64_t)gridDim.x * WI_THREADS) {
+    uint32_t c = 0;
+    if (v < n) {
+      const uint32_t d = indptr[v + 1] - indptr[v];
+      const unsigned long long t = (unsigned long long)d * (d / CKP);
+      if (t >= 0xFFFFFFFFull) atomicOr(too_big, 1u);
+      c = (uint32_t)t;
+    }
+    ckb[v] = c;
+  }
+}
+
 size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 }  // namespace
@@ -526,7 +581,7 @@ static WalkParams wparams(const b2w_graph* g, double p, double q, int extend, co
 
 extern "C" size_t b2w_windex_work_bytes(const b2w_graph* g) {
   if (!g || !(g->flags & B2W_GRAPH_CSR)) return 0;
-  return align256(((size_t)g->nnz + 1) * sizeof(uint32_t)) + b2w_scan::work_bytes(g->nnz + 1) + 256;
+  return align256(((size_t)g->nnz + 1) * sizeof(uint32_t)) + b2w_scan::work_bytes(g->nnz + 1 + g->n) + 512;
 }
 
 static int wcheck(const b2w_graph* g, const void* d_rec, const void* d_bw, const void* d_bq, double p, double q, int extend,
@@ -541,11 +596,11 @@ static int wcheck(const b2w_graph* g, const void* d_rec, const void* d_bw, const
 }
 
 extern "C" int b2w_windex_prepare(const b2w_graph* g, double p, double q, int extend, const float* d_thr, void* d_rec,
-                                  float* d_bw, double* d_bq, void* d_work, size_t work_bytes, uint64_t* h_exc_entries,
-                                  uint64_t* h_ckpt_floats, void* stream) {
+                                  float* d_bw, double* d_bq, uint32_t* d_ckb, void* d_work, size_t work_bytes,
+                                  uint64_t* h_exc_entries, uint64_t* h_ckpt_floats, void* stream) {
   int rc = wcheck(g, d_rec, d_bw, d_bq, p, q, extend, d_thr, "b2w_windex_prepare");
   if (rc) return rc;
-  if (!h_exc_entries || !h_ckpt_floats) { b2w_set_error("b2w_windex_prepare: null output"); return B2W_ERR_INVALID; }
+  if (!h_exc_entries || !h_ckpt_floats || !d_ckb) { b2w_set_error("b2w_windex_prepare: null output"); return B2W_ERR_INVALID; }
   if (!d_work || work_bytes < b2w_windex_work_bytes(g)) { b2w_set_error("b2w_windex_prepare: scratch too small"); return B2W_ERR_INVALID; }
   B2W_CUDA(cudaSetDevice(g->device));
   cudaStream_t s = (cudaStream_t)stream;
@@ -566,9 +621,17 @@ extern "C" int b2w_windex_prepare(const b2w_graph* g, double p, double q, int ex
   const uint64_t count = g->nnz + 1;
   unsigned long long tot_exc = 0, tot_ck = 0;
   B2W_CUDA(b2w_scan::exclusive_scan(count, reinterpret_cast<uint32_t*>(d_rec) + 2, 8, sums, &tot_exc, s));   // .exc
-  B2W_CUDA(b2w_scan::exclusive_scan(count, reinterpret_cast<uint32_t*>(d_rec) + 7, 8, sums, &tot_ck, s));    // .ckp
+  unsigned int* flag = reinterpret_cast<unsigned int*>(reinterpret_cast<char*>(d_work) + work_bytes - 256);
+  B2W_CUDA(cudaMemsetAsync(flag, 0, 4, s));
+  wckpt_count_kernel<<<(unsigned)g->num_sms * 4, WI_THREADS, 0, s>>>(g->n, g->indptr, d_ckb, flag);
+  B2W_CUDA(cudaGetLastError());
+  B2W_CUDA(b2w_scan::exclusive_scan((uint64_t)g->n + 1, d_ckb, 1, sums, &tot_ck, s));
+  unsigned int h_flag = 0;
+  B2W_CUDA(cudaMemcpyAsync(&h_flag, flag, 4, cudaMemcpyDeviceToHost, s));
+  B2W_CUDA(cudaStreamSynchronize(s));
   *h_exc_entries = tot_exc;
   *h_ckpt_floats = tot_ck;
+  if (h_flag) tot_ck = 0xFFFFFFFFull;
   if (tot_exc >= 0xFFFFFFFFull || tot_ck >= 0xFFFFFFFFull) {
     b2w_set_error("b2w_windex_prepare: lists do not fit 32-bit offsets (%llu exceptions, %llu checkpoints)", tot_exc, tot_ck);
     return B2W_ERR_UNSUPPORTED;
@@ -577,11 +640,11 @@ extern "C" int b2w_windex_prepare(const b2w_graph* g, double p, double q, int ex
 }
 
 extern "C" int b2w_windex_finish(b2w_graph* g, double p, double q, int extend, const float* d_thr, void* d_rec,
-                                 float* d_bw, double* d_bq, void* d_exc, uint64_t exc_entries, float* d_ckpt,
-                                 uint64_t ckpt_floats, void* d_work, size_t work_bytes, void* stream) {
+                                 float* d_bw, double* d_bq, const uint32_t* d_ckb, void* d_exc, uint64_t exc_entries,
+                                 float* d_ckpt, uint64_t ckpt_floats, void* d_work, size_t work_bytes, void* stream) {
   int rc = wcheck(g, d_rec, d_bw, d_bq, p, q, extend, d_thr, "b2w_windex_finish");
   if (rc) return rc;
-  if ((exc_entries && !d_exc) || (ckpt_floats && !d_ckpt)) { b2w_set_error("b2w_windex_finish: null list array"); return B2W_ERR_INVALID; }
+  if ((exc_entries && !d_exc) || (ckpt_floats && !d_ckpt) || !d_ckb) { b2w_set_error("b2w_windex_finish: null list array"); return B2W_ERR_INVALID; }
   if (!d_work || work_bytes < b2w_windex_work_bytes(g)) { b2w_set_error("b2w_windex_finish: scratch too small"); return B2W_ERR_INVALID; }
   B2W_CUDA(cudaSetDevice(g->device));
   cudaStream_t s = (cudaStream_t)stream;
@@ -593,10 +656,10 @@ extern "C" int b2w_windex_finish(b2w_graph* g, double p, double q, int extend, c
     if (extend) wedge_kernel<true, true><<<grid, WI_THREADS, 0, s>>>(P, g->nnz, src, rec, d_bw, d_bq, reinterpret_cast<WExc*>(d_exc));
     else wedge_kernel<false, true><<<grid, WI_THREADS, 0, s>>>(P, g->nnz, src, rec, d_bw, d_bq, reinterpret_cast<WExc*>(d_exc));
   }
-  wsum_kernel<<<(unsigned)g->num_sms * 16, WI_THREADS, 0, s>>>(g->nnz, rec, d_bw, reinterpret_cast<const WExc*>(d_exc), d_ckpt);
+  wsum_kernel<<<(unsigned)g->num_sms * 16, WI_THREADS, 0, s>>>(g->nnz, rec, d_bw, reinterpret_cast<const WExc*>(d_exc), d_ckb, d_ckpt);
   B2W_CUDA(cudaGetLastError());
   B2W_CUDA(cudaStreamSynchronize(s));                                 // complete before any walk may use it
-  g->w_rec = d_rec; g->w_exc = d_exc; g->w_bw = d_bw; g->w_bq = d_bq; g->w_ckpt = d_ckpt;
+  g->w_rec = d_rec; g->w_exc = d_exc; g->w_bw = d_bw; g->w_bq = d_bq; g->w_ckpt = d_ckpt; g->w_ckb = d_ckb;
   g->w_p = p; g->w_q = q; g->w_extend = extend ? 1 : 0; g->w_thr = extend ? d_thr : nullptr;
   g->flags |= B2W_GRAPH_HAS_WINDEX;
   return B2W_OK;
@@ -619,7 +682,7 @@ int b2w_launch_wedge(const b2w_graph* g, const WalkParams& P, cudaStream_t s) {
   WConsts C;
   C.rec = reinterpret_cast<const WRec*>(g->w_rec);
   C.exc = reinterpret_cast<const WExc*>(g->w_exc);
-  C.bw = g->w_bw; C.bq = g->w_bq; C.ckpt = g->w_ckpt;
+  C.bw = g->w_bw; C.bq = g->w_bq; C.ckpt = g->w_ckpt; C.ckb = g->w_ckb;
   C.extend = P.extend;
   // f64 evaluation of P(k): (deg + #exceptions + 2) additions of magnitude <= R * P(k), R = the largest ratio between
   // a base weight and the weight that replaces it (the deviations may cancel most of a prefix)

@@ -255,22 +255,25 @@ class WalkEngine:
             bw = torch.empty(max(nnz, 1), dtype=torch.float32, device=self.device)
             bq = torch.empty(max(nnz, 1), dtype=torch.float64, device=self.device)
             work = torch.empty(wb, dtype=torch.uint8, device=self.device)
+            ckb = torch.empty(gi.num_nodes + 1, dtype=torch.int32, device=self.device)
             n_exc, n_ck = C.c_uint64(0), C.c_uint64(0)
             thr = _ptr(self.thr if extend else None)
             rc = self.lib.b2w_windex_prepare(self.handle, float(p), float(q), int(bool(extend)), thr, _ptr(rec), _ptr(bw),
-                                             _ptr(bq), _ptr(work), wb, C.byref(n_exc), C.byref(n_ck), C.c_void_p(stream))
+                                             _ptr(bq), _ptr(ckb), _ptr(work), wb, C.byref(n_exc), C.byref(n_ck),
+                                             C.c_void_p(stream))
             if rc == capi.ERR_UNSUPPORTED or (rc == capi.OK and 24 * n_exc.value + 4 * n_ck.value > 0.5 * free):
                 return False
             capi.check(rc, "b2w_windex_prepare")
             exc = torch.empty(3 * max(int(n_exc.value), 1), dtype=torch.int64, device=self.device)
             ck = torch.empty(max(int(n_ck.value), 1), dtype=torch.float32, device=self.device)
             capi.check(self.lib.b2w_windex_finish(self.handle, float(p), float(q), int(bool(extend)), thr, _ptr(rec),
-                                                  _ptr(bw), _ptr(bq), _ptr(exc), int(n_exc.value), _ptr(ck),
+                                                  _ptr(bw), _ptr(bq), _ptr(ckb), _ptr(exc), int(n_exc.value), _ptr(ck),
                                                   int(n_ck.value), _ptr(work), wb, C.c_void_p(stream)), "b2w_windex_finish")
             t1.record()
             t1.synchronize()
             self.windex_ms = t0.elapsed_time(t1)
         self._keep["w_rec"], self._keep["w_bw"], self._keep["w_bq"], self._keep["w_exc"], self._keep["w_ckpt"] = rec, bw, bq, exc, ck
+        self._keep["w_ckb"] = ckb
         self._windex_key = key
         self.windex_bytes = 32 * (nnz + 1) + 12 * nnz + 24 * int(n_exc.value) + 4 * int(n_ck.value)
         self.windex_counts = dict(exceptions=int(n_exc.value), checkpoints=int(n_ck.value))
@@ -279,7 +282,7 @@ class WalkEngine:
     def drop_windex(self):
         if self.kind == "csr" and self.handle:
             capi.check(self.lib.b2w_graph_clear_windex(self.handle), "b2w_graph_clear_windex")
-        for k in ("w_rec", "w_bw", "w_bq", "w_exc", "w_ckpt"):
+        for k in ("w_rec", "w_bw", "w_bq", "w_exc", "w_ckpt", "w_ckb"):
             self._keep.pop(k, None)
         self._windex_key = None
 

@@ -101,7 +101,7 @@ def test_windex_content(case):
         assert np.allclose(bq[s:e], np.cumsum(bw[s:e].astype(np.float64)), rtol=1e-13, atol=0)
     assert rec.shape[0] == nnz + 1
     for e, w in enumerate(want):
-        nxt, kpf, off, deg, cs, S, vkp, ckp = (int(v) for v in rec[e])
+        nxt, kpf, off, deg, cs, S, vkp, bkp = (int(v) for v in rec[e])
         assert (nxt, deg, cs) == (w["nxt"], w["deg"], w["cs"]), e
         if deg == 0:
             continue
@@ -110,6 +110,7 @@ def test_windex_content(case):
         assert S == int(w["S"].view(np.uint32)), (e, np.uint32(S).view(f32), w["S"])
         if w["found"]:
             assert vkp == int(w["vkp"].view(np.uint32)), e
+            assert bkp == int(want_bw[cs + w["pos"]].view(np.uint32)), e
         if w["exc"]:
             hdr = exc[off]
             assert int(hdr[:4].view(np.uint32)[0]) == len(w["exc"]), e

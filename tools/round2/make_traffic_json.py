@@ -15,8 +15,9 @@ for f in sorted(glob.glob("gpurun_out/traffic_*.csv")):
         scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "ms": 1e-3, "us": 1e-6, "s": 1, "ns": 1e-9}.get(u, 1)
         m[r[i_name]] = v * scale
         kern = r[i_k]
-    name = kern.split("::")[-1].split("<")[0].split("(")[0]
-    if "walk_thread_kernel" in kern:
+    import re
+    name = re.search(r"walk_\w+", kern).group(0)
+    if name == "walk_thread_kernel":
         name = "walk_thread_kernel<PRECOMP>"
     rec = {"kernel": name, "dram_bytes_per_launch": int(m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]),
            "dram_read_bytes": int(m["dram__bytes_read.sum"]), "dram_write_bytes": int(m["dram__bytes_write.sum"]),
