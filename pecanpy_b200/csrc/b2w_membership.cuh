@@ -140,12 +140,12 @@ __device__ __forceinline__ void lower_bound_eq_xN(const uint32_t* __restrict__ r
 #define B2W_CHUNKS_WARP 2      /* 32-lane groups */
 #endif
 #ifndef B2W_INREG_MEMBERSHIP
-#define B2W_INREG_MEMBERSHIP 0 /* 32-lane groups, both rows <= 32 entries: search row(prev) in registers with shuffles.
-                                  Written at the end of round 1 from the cost model; NOT yet run on a GPU -- off */
+#define B2W_INREG_MEMBERSHIP 1 /* 32-lane groups, both rows <= 32 entries: search row(prev) in registers with shuffles.
+                                  Round 2 A/B on the B200: parity-green (235 tests), 2.04 -> 2.06 G steps/s on config #3 */
 #endif
 #ifndef B2W_SUBWARP_REDUX
-#define B2W_SUBWARP_REDUX 0   /* sub-warp groups, rows <= 32: assemble the bitmap word with one REDUX.OR.  Parity-green on
-                                  the B200 (uw-g8 / uw-g16 suites, 88 tests) but NOT yet timed -- off until measured */
+#define B2W_SUBWARP_REDUX 1   /* sub-warp groups, rows <= 32: assemble the bitmap word with one REDUX.OR.  Round 2 A/B on the
+                                  B200: parity-green, 5.38 -> 6.11 G steps/s on config #2 (index-free kernel) */
 #endif
 #ifndef B2W_CHUNKS_SUBWARP
 #define B2W_CHUNKS_SUBWARP 0   /* sub-warp groups: 0 = 32 / G (one bitmap word per iteration) */

@@ -7,6 +7,7 @@
 // Reference: pecanpy.py:164-210 (_random_walks), :409-438 (PreComp.move_forward),
 // :304-307 (FirstOrderUnweighted), :327-332 (PreCompFirstOrder), :668-677 (alias_draw).
 #include "b2w_probs.cuh"
+#include "b2w_rowout.cuh"
 
 namespace {
 
@@ -27,16 +28,18 @@ __device__ __forceinline__ uint32_t alias_draw(const uint32_t* __restrict__ j, c
 // what it wants is warps in flight, not registers.
 template <int MODE, bool EXTEND, int MINB>
 __global__ void __launch_bounds__(256, MINB) walk_thread_kernel(const WalkParams P) {
+  __shared__ uint32_t s_stage[8 * 256];                                // rows leave as complete 32-byte sectors (b2w_rowout.cuh)
   const uint32_t L = P.L;
   uint64_t steps = 0, overflow = 0;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < P.n_rows;
        i += (uint64_t)gridDim.x * blockDim.x) {
-    uint32_t* out = P.out + i * P.ld_out;
+    RowWriter<256> out;
+    out.begin(P.out + i * P.ld_out, s_stage);
     const uint64_t row = P.row0 + i;
     uint32_t cur = P.start[i];
     uint32_t prev = 0;
     uint32_t eff = L + 1;
-    out[0] = cur;
+    out.push(0, cur);
     uint32_t j = 1;
     for (; j <= L; ++j) {
       uint32_t cs = P.indptr[cur];
@@ -72,13 +75,14 @@ __global__ void __launch_bounds__(256, MINB) walk_thread_kernel(const WalkParams
         }
       }
       uint32_t nxt = P.indices[cs + choice];
-      out[j] = nxt;
+      out.push(j, nxt);
       prev = cur;
       cur = nxt;
       ++steps;
     }
-    for (uint32_t z = j; z <= L; ++z) out[z] = 0;                      // zero tail (np.zeros, :182)
-    out[L + 1] = eff;
+    for (uint32_t z = j; z <= L; ++z) out.push(z, 0u);                 // zero tail (np.zeros, :182)
+    out.push(L + 1, eff);
+    out.finish(L + 2);
   }
   if (P.stats && !(P.flags & B2W_FLAG_NO_FILTER_STATS)) {
     // one atomic per warp
