@@ -311,8 +311,13 @@ def run_workload(name, args, K, W, rank, world, local_rank, *, do_e2e=True, do_c
     tot_pad = B * world * NB
     peer, gather = None, "none"
     if world > 1:
-        gather = args.gather
-        if gather == "push":
+        # auto: the all-gather fused into the walk kernel (mirrored stores) where the kernel can do it -- measured
+        # 2 GPUs 68-70 G vs 62 G (NCCL), 4 GPUs 113 G vs 88 G; at 8 GPUs (the coalesced variant has not been measured
+        # there) a short probe in the warm-up decides between it and NCCL
+        gather = "mirror" if args.gather == "auto" else args.gather
+        if gather == "mirror" and (world > 8 or eng.prepare(wl["mode"], wl["p"], wl["q"], wl["extend"], args.flags) != "walk_uw_edge_kernel"):
+            gather = "nccl"                                 # only the unweighted edge-index kernel mirrors its rows
+        if gather in ("push", "mirror"):
             from pecanpy_b200.dist import PeerMatrix
             peer = PeerMatrix(tot_pad, ld, dev)             # collective; .ok is agreed between the ranks
             if not peer.ok:                                 # no CUDA IPC / peer access on this box: NCCL does it
@@ -338,8 +343,11 @@ def run_workload(name, args, K, W, rank, world, local_rank, *, do_e2e=True, do_c
         for b, (r0, rows) in enumerate(blocks):
             if rows:
                 eng.walk(wl["mode"], wl["p"], wl["q"], d_start_all[r0:r0 + rows], L, seed=seed, extend=wl["extend"],
-                         row0=r0, out=full[r0:r0 + rows], flags=args.flags, collect_stats=False)
-            if peer is not None:
+                         row0=r0, out=full[r0:r0 + rows], flags=args.flags, collect_stats=False,
+                         mirrors=peer.mirror_ptrs(r0) if gather == "mirror" else None)
+            if gather == "mirror":
+                pass                                        # the kernel stored the rows in every peer's matrix itself
+            elif gather == "push":
                 peer.push(r0, r0 + rows)
             elif world > 1:
                 comm.wait_stream(cur)
@@ -348,11 +356,30 @@ def run_workload(name, args, K, W, rank, world, local_rank, *, do_e2e=True, do_c
                     dist.all_gather_into_tensor(seg.view(-1), full[(b * world + rank) * B:(b * world + rank + 1) * B].view(-1))
         if events is not None:
             events[1].record(cur)                           # this rank's walk kernels are done
-        if peer is not None:
+        if gather in ("mirror", "push"):
             peer.finish()
         elif world > 1:
             cur.wait_stream(comm)
 
+    if world > 4 and args.gather == "auto" and gather == "mirror":
+        probe = {}
+        for cand in ("mirror", "nccl"):                     # (NCCL gathers into the same, IPC-shared, matrix)
+            gather = cand
+            one_pass(900)
+            torch.cuda.synchronize()
+            barrier()
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            one_pass(901)
+            one_pass(902)
+            p1.record()
+            torch.cuda.synchronize()
+            pt = torch.tensor([p0.elapsed_time(p1) / 2], dtype=torch.float64, device=dev)
+            dist.all_reduce(pt, op=dist.ReduceOp.MAX)       # the same number, hence the same choice, on every rank
+            probe[cand] = float(pt[0])
+        gather = "mirror" if probe["mirror"] <= probe["nccl"] else "nccl"
+        extras["gather_probe_ms"] = probe
+        log(f"[bench] rank {rank}: gather probe {probe} -> {gather}")
     for it in range(W):
         one_pass(1000 + it)
     torch.cuda.synchronize()
@@ -505,7 +532,7 @@ def run_workload(name, args, K, W, rank, world, local_rank, *, do_e2e=True, do_c
         line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": 1e3 * t_total / max(K_eff, 1), "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": dtype_of(wl), "data": "synthetic",
-                "config": config_of(args, name, wl, g, world, NB, {"push": "copy engines over NVLink into CUDA-IPC mapped peer matrices", "nccl": "NCCL", "none": ""}[gather]), "clocks": clocks, "gpu_launches": launches,
+                "config": config_of(args, name, wl, g, world, NB, {"push": "copy engines over NVLink into CUDA-IPC mapped peer matrices", "mirror": "fused: the walk kernel stores every row sector into the CUDA-IPC mapped matrices of all peers over NVLink", "nccl": "NCCL", "none": ""}[gather]), "clocks": clocks, "gpu_launches": launches,
                 "timed_passes": K_eff, "steps_per_pass": steps_job,
                 "kernel_ms_max_over_ranks": 1e3 * t_kernel_max / max(K_eff, 1),
                 "checksum": {"seed": CHECK_SEED, "fnv_like_u64": checksum},
@@ -593,8 +620,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the sub-benchmarks of the other BASELINE configs")
     ap.add_argument("--batches", type=int, default=0, help="N > 1: all-gather batches overlapped with the walk (0 = auto)")
-    ap.add_argument("--gather", default="nccl", choices=["push", "nccl"],
-                    help="N > 1: copy-engine pushes into the peers' matrices (CUDA IPC) or NCCL all-gather")
+    ap.add_argument("--gather", default="auto", choices=["auto", "push", "nccl", "mirror"],
+                    help="N > 1: how every rank gets the whole matrix -- mirror: the walk kernel stores its rows into the peers' matrices itself (CUDA IPC over NVLink); push: copy engines; nccl: all-gather; auto: mirror where the kernel supports it (probe against nccl beyond 4 GPUs)")
     ap.add_argument("--flags", type=int, default=0, help="b2w_walk flags (debug)")
     args = ap.parse_args()
 

@@ -283,6 +283,17 @@ int b2w_walk(const b2w_graph* g, int mode, double p, double q, int extend, const
              uint64_t seed, int rng_mode, const double* d_feed, uint32_t* d_out, uint64_t ld_out,
              void* d_work, size_t work_bytes, b2w_walk_stats* d_stats, uint32_t flags, void* stream);
 
+/* b2w_walk with the all-gather FUSED into the kernel (multi-process jobs on one node): every row the kernel writes to
+ * d_out is also stored, sector by sector as it is produced, at the same place of up to 7 other matrices --
+ * d_mirrors[k] = the address in peer k's matrix that corresponds to d_out (mapped with b2w_shared_open; congruent to
+ * d_out modulo 32 bytes).  The stores travel over NVLink while the walk goes on; when the kernel has finished on every
+ * rank (stream sync + a barrier) every matrix holds every row, without a gather phase.  Philox regime only.  Served by
+ * the unweighted SparseOTF edge-index kernel; other modes return B2W_ERR_UNSUPPORTED (use b2w_walk + an all-gather). */
+int b2w_walk_mirrored(const b2w_graph* g, int mode, double p, double q, int extend, const float* d_thr,
+                      const uint32_t* d_start, uint64_t row0, uint64_t n_rows, uint32_t walk_length, uint64_t seed,
+                      uint32_t* d_out, uint64_t ld_out, void* d_work, size_t work_bytes, b2w_walk_stats* d_stats,
+                      uint32_t flags, void* stream, int n_mirrors, uint32_t* const* d_mirrors);
+
 /* Name of the kernel b2w_walk would launch for these arguments (static string; for logs/benchmarks). */
 const char* b2w_walk_kernel_name(const b2w_graph* g, int mode, double p, double q, int extend, uint32_t flags);
 
@@ -328,6 +339,9 @@ int b2w_shared_open(int device, const unsigned char handle[64], void** d_ptr);
 int b2w_shared_close(int device, void* d_ptr);
 int b2w_push_rows(int device, void* const* d_peers, int n_peers, int self, uint64_t row_lo, uint64_t rows,
                   uint64_t row_bytes, void* stream);
+/* the same with one stream per peer (streams[p] for p != self): copies to different peers run concurrently */
+int b2w_push_rows_streams(int device, void* const* d_peers, int n_peers, int self, uint64_t row_lo, uint64_t rows,
+                          uint64_t row_bytes, void* const* streams);
 
 /* Sum of (effective_length - 1) over the rows of a device walk matrix (the metric's unit). */
 int b2w_count_steps(const uint32_t* d_out, uint64_t n_rows, uint32_t walk_length, uint64_t ld_out,

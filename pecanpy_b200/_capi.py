@@ -43,8 +43,8 @@ EXPORTS = [
     "b2w_edgelist_parse", "b2w_edgelist_fetch", "b2w_edgelist_free",
     "b2w_edge_ckpt_work_bytes", "b2w_edge_ckpt_prepare", "b2w_edge_ckpt_finish", "b2w_graph_clear_edge_ckpt",
     "b2w_windex_work_bytes", "b2w_windex_prepare", "b2w_windex_finish", "b2w_graph_clear_windex",
-    "b2w_shared_alloc", "b2w_shared_free", "b2w_shared_open", "b2w_shared_close", "b2w_push_rows",
-    "b2w_walk_multi", "b2w_alias_build_packed", "b2w_graph_set_alias_packed",
+    "b2w_shared_alloc", "b2w_shared_free", "b2w_shared_open", "b2w_shared_close", "b2w_push_rows", "b2w_push_rows_streams",
+    "b2w_walk_multi", "b2w_walk_mirrored", "b2w_alias_build_packed", "b2w_graph_set_alias_packed",
     "b2w_edge_index_work_bytes", "b2w_edge_index_prepare", "b2w_edge_index_finish", "b2w_graph_set_edge_index",
 ]
 
@@ -94,6 +94,8 @@ def lib():
     L.b2w_walk_work_bytes.argtypes = [vp, i32]
     L.b2w_walk_work_bytes.restype = sz
     L.b2w_walk.argtypes = [vp, i32, dbl, dbl, i32, vp, vp, u64, u64, u32, u64, i32, vp, vp, u64, vp, sz, vp, u32, vp]
+    L.b2w_walk_mirrored.argtypes = [vp, i32, dbl, dbl, i32, vp, vp, u64, u64, u32, u64, vp, u64, vp, sz, vp, u32, vp, i32,
+                                    C.POINTER(vp)]
     L.b2w_walk_host.argtypes = [vp, i32, dbl, dbl, i32, vp, vp, u64, u64, u32, u64, vp, u64, C.POINTER(WalkStats), u32]
     L.b2w_walk_multi.argtypes = [i32, C.POINTER(vp), i32, dbl, dbl, i32, C.POINTER(vp), vp, u64, u32, u64, vp, u64,
                                  C.POINTER(WalkStats), u32]
@@ -112,6 +114,7 @@ def lib():
     L.b2w_shared_open.argtypes = [i32, C.c_char_p, C.POINTER(vp)]
     L.b2w_shared_close.argtypes = [i32, vp]
     L.b2w_push_rows.argtypes = [i32, C.POINTER(vp), i32, i32, u64, u64, u64, vp]
+    L.b2w_push_rows_streams.argtypes = [i32, C.POINTER(vp), i32, i32, u64, u64, u64, C.POINTER(vp)]
     L.b2w_walk_kernel_name.argtypes = [vp, i32, dbl, dbl, i32, u32]
     L.b2w_walk_kernel_name.restype = C.c_char_p
     L.b2w_noise_thresholds.argtypes = [vp, dbl, vp, vp]

@@ -280,10 +280,40 @@ extern "C" size_t b2w_walk_work_bytes(const b2w_graph* g, int mode) {
   return 0;
 }
 
+static int walk_impl(const b2w_graph* g, int mode, double p, double q, int extend, const float* d_thr,
+                     const uint32_t* d_start, uint64_t row0, uint64_t n_rows, uint32_t walk_length,
+                     uint64_t seed, int rng_mode, const double* d_feed, uint32_t* d_out, uint64_t ld_out,
+                     void* d_work, size_t work_bytes, b2w_walk_stats* d_stats, uint32_t flags, void* stream,
+                     int n_mirrors, uint32_t* const* d_mirrors);
+
 extern "C" int b2w_walk(const b2w_graph* g, int mode, double p, double q, int extend, const float* d_thr,
                         const uint32_t* d_start, uint64_t row0, uint64_t n_rows, uint32_t walk_length,
                         uint64_t seed, int rng_mode, const double* d_feed, uint32_t* d_out, uint64_t ld_out,
                         void* d_work, size_t work_bytes, b2w_walk_stats* d_stats, uint32_t flags, void* stream) {
+  return walk_impl(g, mode, p, q, extend, d_thr, d_start, row0, n_rows, walk_length, seed, rng_mode, d_feed, d_out, ld_out,
+                   d_work, work_bytes, d_stats, flags, stream, 0, nullptr);
+}
+
+extern "C" int b2w_walk_mirrored(const b2w_graph* g, int mode, double p, double q, int extend, const float* d_thr,
+                                 const uint32_t* d_start, uint64_t row0, uint64_t n_rows, uint32_t walk_length,
+                                 uint64_t seed, uint32_t* d_out, uint64_t ld_out, void* d_work, size_t work_bytes,
+                                 b2w_walk_stats* d_stats, uint32_t flags, void* stream, int n_mirrors,
+                                 uint32_t* const* d_mirrors) {
+  if (n_mirrors < 0 || n_mirrors > 7 || (n_mirrors && !d_mirrors)) { b2w_set_error("b2w_walk_mirrored: 0..7 mirrors"); return B2W_ERR_INVALID; }
+  for (int k = 0; k < n_mirrors; ++k)
+    if (!d_mirrors[k] || ((reinterpret_cast<uintptr_t>(d_mirrors[k]) ^ reinterpret_cast<uintptr_t>(d_out)) & 31)) {
+      b2w_set_error("b2w_walk_mirrored: mirror %d is null or not congruent to d_out modulo 32 bytes", k);
+      return B2W_ERR_INVALID;
+    }
+  return walk_impl(g, mode, p, q, extend, d_thr, d_start, row0, n_rows, walk_length, seed, B2W_RNG_PHILOX, nullptr, d_out,
+                   ld_out, d_work, work_bytes, d_stats, flags, stream, n_mirrors, d_mirrors);
+}
+
+static int walk_impl(const b2w_graph* g, int mode, double p, double q, int extend, const float* d_thr,
+                     const uint32_t* d_start, uint64_t row0, uint64_t n_rows, uint32_t walk_length,
+                     uint64_t seed, int rng_mode, const double* d_feed, uint32_t* d_out, uint64_t ld_out,
+                     void* d_work, size_t work_bytes, b2w_walk_stats* d_stats, uint32_t flags, void* stream,
+                     int n_mirrors, uint32_t* const* d_mirrors) {
   if (!g) { b2w_set_error("b2w_walk: null graph"); return B2W_ERR_INVALID; }
   if (n_rows == 0) return B2W_OK;
   if (!d_start || !d_out) { b2w_set_error("b2w_walk: null start/out"); return B2W_ERR_INVALID; }
@@ -327,7 +357,15 @@ extern "C" int b2w_walk(const b2w_graph* g, int mode, double p, double q, int ex
   P.rng_mode = rng_mode; P.extend = ext ? 1 : 0;
   b2w_fill_bias_params(P, p, q);
   P.flags = flags; P.work = (float*)d_work; P.stats = d_stats;
+  P.n_mirrors = n_mirrors;
+  for (int k = 0; k < n_mirrors; ++k) P.mirror_delta[k] = (long long)(d_mirrors[k] - d_out);
   cudaStream_t s = (cudaStream_t)stream;
+  if (n_mirrors) {
+    // only the kernel that writes its rows through RowWriter mirrors them (unweighted SparseOTF with the edge index)
+    const bool ok = warp_kernel && !ext && !(flags & B2W_FLAG_NO_UNWEIGHTED_KERNEL) && b2w_uw_eligible(g, p, q) &&
+                    (g->flags & B2W_GRAPH_HAS_EDGE_INDEX) && !(flags & (B2W_FLAG_NO_EDGE_INDEX | B2W_FLAG_COOP)) && !((flags >> 8) & 0xFF);
+    if (!ok) { b2w_set_error("b2w_walk_mirrored: this mode / graph is not served by a mirroring kernel (use b2w_walk + an all-gather)"); return B2W_ERR_UNSUPPORTED; }
+  }
   if (dense) return b2w_launch_dense(g, ext, P, s);
   if (warp_kernel) {
     // unweighted graphs with exactly representable biases: the membership-bitmap kernel

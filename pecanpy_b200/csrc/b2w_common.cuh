@@ -83,6 +83,9 @@ struct WalkParams {
   uint32_t work_stride;   // floats per warp
   unsigned long long* counter;  // dynamic row queue
   b2w_walk_stats* stats;
+  // mirrors of the output rows in the other GPUs' matrices (b2w_walk_mirrored): out + mirror_delta[q], in words
+  long long mirror_delta[7];
+  int n_mirrors;
 };
 
 // ---------------------------------------------------------------- Philox4x32-10

@@ -43,3 +43,49 @@ struct RowWriter {
     for (uint32_t t = count - rem; t < count; ++t) out[t] = stage[((ph + t) & 7u) * THREADS];
   }
 };
+
+// Mirrors: the same rows of the walk matrices of the OTHER GPUs of the job (mapped through CUDA IPC, b2w_shared_open),
+// written by the walk kernel itself over NVLink while it walks -- the all-gather fused into the kernel
+// (b2w_walk_mirrored).  WalkParams::mirror_delta[q] = (peer q's matrix) - (this GPU's matrix) in 4-byte words, all
+// congruent modulo 32 bytes.
+//
+// 32-byte stores by single lanes (RowWriter) are a poor fit for the link: measured 130-150 GB/s of egress per GPU
+// (2 GPUs: +1.6 ms on a 9.8 ms kernel; 8 GPUs: 21.7 ms instead of 2.8).  WarpRowTile stages the rows of the warp's 32
+// walkers in shared memory instead (a ring of 32 words per walker, padded to 33: conflict free both ways) and, every
+// MIRROR_PERIOD steps, the WHOLE WARP writes each walker's new words as one coalesced store of up to 31 consecutive
+// words -- whole 32-byte sectors, cut at the sector boundaries of that row's address -- to the local matrix and to every
+// mirror.  Must be called by the 32 converged lanes of the warp.
+constexpr uint32_t MIRROR_PERIOD = 24;      // words between flushes; + up to 7 carried words <= 31 < ring of 32
+
+struct WarpRowTile {
+  uint32_t* tile;      // this warp's [32][33] words
+  uint64_t row0;       // first row of the warp (lane 0's), in rows of the local matrix
+  uint32_t n;          // rows of the warp that exist (a prefix of the lanes)
+  uint32_t flushed;    // `have` of the last flush (0: none yet)
+
+  __device__ __forceinline__ void begin(uint32_t* warp_tile, const uint64_t first_row, const uint32_t n_rows) {
+    tile = warp_tile; row0 = first_row; n = n_rows; flushed = 0;
+  }
+  __device__ __forceinline__ void put(const uint32_t j, const uint32_t v) { tile[(threadIdx.x & 31) * 33 + (j & 31)] = v; }
+  // words [0, have) of every row have been put; `last`: the rows are complete
+  __device__ __forceinline__ void flush(const WalkParams& P, const uint32_t have, const bool last) {
+    __syncwarp();
+    const uint32_t lane = threadIdx.x & 31;
+    const uint64_t obase = (uint64_t)(reinterpret_cast<uintptr_t>(P.out) >> 2);
+    for (uint32_t w = 0; w < n; ++w) {
+      const uint64_t rb = (row0 + w) * P.ld_out;
+      const uint32_t ph = (uint32_t)((obase + rb) & 7u);
+      const uint32_t a = flushed ? flushed - ((ph + flushed) & 7u) : 0u;      // (flushed >= MIRROR_PERIOD > 7)
+      const uint32_t b = last ? have : have - ((ph + have) & 7u);
+      const uint32_t t = a + lane;
+      if (t < b) {
+        const uint32_t v = tile[w * 33 + (t & 31)];
+        uint32_t* const o = P.out + rb + t;
+        __stcs(o, v);
+        for (int q = 0; q < P.n_mirrors; ++q) __stcs(o + P.mirror_delta[q], v);
+      }
+    }
+    flushed = have;
+    __syncwarp();
+  }
+};

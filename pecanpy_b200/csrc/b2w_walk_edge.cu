@@ -271,13 +271,20 @@ __global__ void __launch_bounds__(EW_THREADS) edge_ckpt_count_kernel(const uint3
 // whole warp (b2w_offedge.cuh) instead of stalling it behind one lane.
 // COOP = false (graphs whose longest row is short): plain per-lane loops, the off-edge step by its own lane -- keeping
 // the warp converged costs ~12 % there (ER config #2: 92 vs 81 G steps/s) and buys nothing.
-template <int MINB, bool COOP>
+// MIRROR = true (multi-GPU jobs, b2w_walk_mirrored; always with COOP): every row is also stored into the same rows of
+// the other GPUs' matrices over NVLink while the walk goes on -- the all-gather fused into the walk.  The rows leave
+// through WarpRowTile (b2w_rowout.cuh): coalesced warp stores of up to 31 words per row every 24 steps.
+template <int MINB, bool COOP, bool MIRROR>
 __global__ void __launch_bounds__(EW_THREADS, MINB) walk_uw_edge_kernel(const WalkParams P, const EdgeConsts C) {
-  __shared__ uint32_t s_stage[8 * EW_THREADS];
+  static_assert(COOP || !MIRROR, "mirrored stores need the converged loops");
+  __shared__ uint32_t s_stage[(MIRROR ? 33 : 8) * EW_THREADS];
   const uint32_t L = P.L;
   const uint32_t lane = threadIdx.x & 31;
   uint32_t st_steps = 0, st_replays = 0, st_overflow = 0;
+#define B2W_PUSH(jj, vv) do { if (MIRROR) tilew.put(jj, vv); else row.push(jj, vv); } while (0)
+#define B2W_FINISH(cc) do { if (!MIRROR) row.finish(cc); } while (0)
   if (!COOP) {
+    WarpRowTile tilew;                                                // (unused here: MIRROR implies COOP)
     const float w_out = __fmul_rn(__int2float_rn(C.a_out), C.g), w_ret = __fmul_rn(__int2float_rn(C.a_ret), C.g);
     for (uint64_t i = blockIdx.x * (uint64_t)EW_THREADS + threadIdx.x; i < P.n_rows; i += (uint64_t)gridDim.x * EW_THREADS) {
       RowWriter<EW_THREADS> row;
@@ -287,7 +294,7 @@ __global__ void __launch_bounds__(EW_THREADS, MINB) walk_uw_edge_kernel(const Wa
       uint32_t d = __ldg(P.indptr + cur + 1) - cs;
       uint32_t kpf = 0, toff = 0, eff = L + 1;
       bool edge_ok = true;                                            // the walker arrived over a stored edge
-      row.push(0, cur);
+      B2W_PUSH(0, cur);
       uint32_t j = 1;
       for (; j <= L; ++j) {
         if (d == 0) { eff = j; break; }                               // pecanpy.py:194-196, 204-206
@@ -300,26 +307,29 @@ __global__ void __launch_bounds__(EW_THREADS, MINB) walk_uw_edge_kernel(const Wa
         const uint4 r = __ldg(C.rec + (cs + choice));                 // [cs + d] is the next row's first edge: pecanpy.py:559
         prev = cur;
         cur = r.x; kpf = r.y; toff = r.z; d = r.w;
-        row.push(j, cur);
+        B2W_PUSH(j, cur);
         cs = __ldg(P.indptr + cur);
       }
       st_steps += eff - 1;
-      for (uint32_t z = j; z <= L; ++z) row.push(z, 0u);              // zero tail (np.zeros, pecanpy.py:182)
-      row.push(L + 1, eff);
-      row.finish(L + 2);
+      for (uint32_t z = j; z <= L; ++z) B2W_PUSH(z, 0u);              // zero tail (np.zeros, pecanpy.py:182)
+      B2W_PUSH(L + 1, eff);
+      B2W_FINISH(L + 2);
     }
   }
   for (uint64_t i = blockIdx.x * (uint64_t)EW_THREADS + threadIdx.x; COOP && __any_sync(B2W_FULL, i < P.n_rows);
        i += (uint64_t)gridDim.x * EW_THREADS) {
     const bool alive = i < P.n_rows;
     RowWriter<EW_THREADS> row;
+    WarpRowTile tilew;
+    if (MIRROR) tilew.begin(s_stage + (threadIdx.x >> 5) * (33 * 32), i - lane, (uint32_t)min((uint64_t)32, P.n_rows - (i - lane)));
+    uint32_t since = 1;                                               // words put since the last flush
     uint32_t cur = 0, prev = 0, cs = 0, d = 0;
     if (alive) {
-      row.begin(P.out + i * P.ld_out, s_stage);
+      if (!MIRROR) row.begin(P.out + i * P.ld_out, s_stage);
       cur = __ldg(P.start + i);
       cs = __ldg(P.indptr + cur);
       d = __ldg(P.indptr + cur + 1) - cs;
-      row.push(0, cur);
+      B2W_PUSH(0, cur);
     }
     uint32_t kpf = 0, toff = 0, eff = L + 1;
     bool walking = alive;
@@ -350,13 +360,15 @@ __global__ void __launch_bounds__(EW_THREADS, MINB) walk_uw_edge_kernel(const Wa
         cur = r.x; kpf = r.y; toff = r.z; d = r.w;
         cs = __ldg(P.indptr + cur);
       }
-      if (alive) row.push(j, walking ? cur : 0u);                     // zero tail after a dead end (np.zeros, pecanpy.py:182)
+      if (alive) B2W_PUSH(j, walking ? cur : 0u);                     // zero tail after a dead end (np.zeros, pecanpy.py:182)
+      if (MIRROR && ++since == MIRROR_PERIOD) { tilew.flush(P, j + 1, false); since = 0; }
     }
     if (alive) {
       st_steps += eff - 1;
-      row.push(L + 1, eff);
-      row.finish(L + 2);
+      B2W_PUSH(L + 1, eff);
+      B2W_FINISH(L + 2);
     }
+    if (MIRROR) tilew.flush(P, L + 2, true);
   }
   if (P.stats && !(P.flags & B2W_FLAG_NO_FILTER_STATS)) {
     for (int o = 16; o; o >>= 1) {
@@ -371,6 +383,8 @@ __global__ void __launch_bounds__(EW_THREADS, MINB) walk_uw_edge_kernel(const Wa
     }
   }
 }
+#undef B2W_PUSH
+#undef B2W_FINISH
 
 // ---------------------------------------------------------------------------------------------------
 // PreComp through the per-edge index.  The reference's step (pecanpy.py:427-438) bisects prev in row(cur) to find
@@ -515,10 +529,16 @@ int b2w_launch_uw_edge(const b2w_graph* g, const WalkParams& P, cudaStream_t s) 
   bool coop = g->max_degree > 256u;
   if (P.flags & B2W_FLAG_OFFEDGE_WARP) coop = true;
   if (P.flags & B2W_FLAG_OFFEDGE_LANE) coop = false;
+  const bool mirror = P.n_mirrors > 0;
+  if (mirror) coop = true;
 #define B2W_EDGE_LAUNCH(MB)                                                                     \
   do {                                                                                          \
-    if (coop) walk_uw_edge_kernel<MB, true><<<blocks, EW_THREADS, 0, s>>>(P, C);                \
-    else walk_uw_edge_kernel<MB, false><<<blocks, EW_THREADS, 0, s>>>(P, C);                    \
+    if (mirror) {                                                                               \
+      walk_uw_edge_kernel<MB, true, true><<<blocks, EW_THREADS, 0, s>>>(P, C);                  \
+    } else {                                                                                    \
+      if (coop) walk_uw_edge_kernel<MB, true, false><<<blocks, EW_THREADS, 0, s>>>(P, C);       \
+      else walk_uw_edge_kernel<MB, false, false><<<blocks, EW_THREADS, 0, s>>>(P, C);           \
+    }                                                                                           \
   } while (0)
   if (mb == 6) B2W_EDGE_LAUNCH(6);
   else if (mb == 4) B2W_EDGE_LAUNCH(4);

@@ -68,6 +68,10 @@ class PeerMatrix:
             self.full.zero_()
             torch.cuda.current_stream(self.device).synchronize()
             self.stream = torch.cuda.Stream(device=self.device)
+            # one stream per peer: the copies to different peers run on different copy engines at the same time
+            self.streams = [torch.cuda.Stream(device=self.device) if r != self.rank else self.stream
+                            for r in range(self.world)]
+            self._stream_ptrs = (C.c_void_p * self.world)(*[s.cuda_stream for s in self.streams])
         handles = [None] * self.world
         dist.all_gather_object(handles, handle.raw, group=group)
         self._mapped = [None] * self.world
@@ -92,12 +96,22 @@ class PeerMatrix:
         the current stream (the walk of that block)."""
         if hi <= lo or self.world == 1:
             return
-        self.stream.wait_stream(torch.cuda.current_stream(self.device))
-        self.capi.check(self.lib.b2w_push_rows(self.device.index, self._peers, self.world, self.rank, lo, hi - lo,
-                                               self.row_bytes, self.C.c_void_p(self.stream.cuda_stream)), "b2w_push_rows")
+        cur = torch.cuda.current_stream(self.device)
+        for r, st in enumerate(self.streams):
+            if r != self.rank:
+                st.wait_stream(cur)
+        self.capi.check(self.lib.b2w_push_rows_streams(self.device.index, self._peers, self.world, self.rank, lo, hi - lo,
+                                                       self.row_bytes, self._stream_ptrs), "b2w_push_rows_streams")
+
+    def mirror_ptrs(self, row: int) -> list:
+        """Addresses of row ``row`` in every PEER's matrix (for engine.walk(..., mirrors=...): the walk kernel stores
+        its rows there itself, the all-gather fused into the kernel); ``finish`` completes it."""
+        return [p + row * self.row_bytes for r, p in enumerate(self._mapped) if r != self.rank]
 
     def finish(self) -> None:
-        self.stream.synchronize()                              # my copies have landed in the peers
+        for r, st in enumerate(self.streams):                  # my copies have landed in the peers
+            if r != self.rank:
+                st.synchronize()
         dist.all_reduce(self._token, group=self.group)         # ... and everybody else's in mine
         torch.cuda.current_stream(self.device).synchronize()
 
@@ -134,10 +148,11 @@ def sharded_walks(walk_block: Callable[[int, int, torch.Tensor], None], total_ro
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     blocks, B = shard_rows(total_rows, world, rank, batches)
     on_gpu = torch.device(device).type == "cuda"
-    peer = PeerMatrix(B * world * len(blocks), row_len, device, group) if (gather == "push" and on_gpu and world > 1) else None
+    peer = PeerMatrix(B * world * len(blocks), row_len, device, group) if (gather in ("push", "mirror") and on_gpu and world > 1) else None
     if peer is not None and not peer.ok:       # no peer access between these GPUs: NCCL does it
         peer.close()
         peer = None
+    mirror = peer is not None and gather == "mirror" and world <= 8
     if peer is not None:
         full = peer.full
     else:
@@ -147,8 +162,13 @@ def sharded_walks(walk_block: Callable[[int, int, torch.Tensor], None], total_ro
     for b, (lo, hi) in enumerate(blocks):
         slot = (b * world + rank) * B
         if hi > lo:
-            walk_block(lo, hi, full[slot:slot + (hi - lo)])
-        if peer is not None:
+            if mirror:
+                walk_block(lo, hi, full[slot:slot + (hi - lo)], mirrors=peer.mirror_ptrs(slot))
+            else:
+                walk_block(lo, hi, full[slot:slot + (hi - lo)])
+        if mirror:
+            pass                                # the kernel has stored the rows in the peers' matrices itself
+        elif peer is not None:
             peer.push(slot, slot + (hi - lo))
         elif world > 1:
             seg, mine = full[b * world * B:(b + 1) * world * B], full[slot:slot + B]
@@ -178,9 +198,13 @@ def simulate_walks_distributed(engine, mode, p: float, q: float, start, walk_len
     import numpy as np
     start = np.ascontiguousarray(start, dtype=np.uint32)
 
-    def walk_block(lo: int, hi: int, out_block: torch.Tensor) -> None:
+    def walk_block(lo: int, hi: int, out_block: torch.Tensor, mirrors=None) -> None:
         engine.walk(mode, p, q, start[lo:hi], walk_length, seed=seed, extend=extend, row0=lo, out=out_block,
-                    flags=flags, collect_stats=False)
+                    flags=flags, collect_stats=False, mirrors=mirrors)
+
+    if gather == "mirror":                      # only the unweighted SparseOTF edge-index kernel mirrors its rows
+        if engine.prepare(mode, p, q, extend, flags) != "walk_uw_edge_kernel":
+            gather = "push"
 
     return sharded_walks(walk_block, start.size, walk_length + 2, engine.device, group=group, batches=batches,
                          gather=gather)

@@ -390,9 +390,13 @@ class WalkEngine:
     # ------------------------------------------------------------------ walking
     def walk(self, mode, p: float, q: float, start, walk_length: int, seed: int = 0, *, extend: bool = False,
              rng: int = capi.RNG_PHILOX, feed=None, row0: int = 0, flags: int = 0,
-             out: Optional[torch.Tensor] = None, collect_stats: bool = True) -> torch.Tensor:
+             out: Optional[torch.Tensor] = None, collect_stats: bool = True, mirrors=None) -> torch.Tensor:
         """Walk ``len(start)`` rows on this GPU; returns an int32 *view* of the uint32 matrix
-        ``[n_rows, walk_length + 2]`` (layout of reference pecanpy.py:182-206) on the device."""
+        ``[n_rows, walk_length + 2]`` (layout of reference pecanpy.py:182-206) on the device.
+
+        ``mirrors``: device addresses (ints) of the place of ``out`` in up to 7 peer matrices mapped into this process
+        (dist.PeerMatrix.mirror_ptrs): the kernel stores every row there too, over NVLink, while it walks
+        (b2w_walk_mirrored; raises for kernels that do not mirror)."""
         mode = MODES[mode] if isinstance(mode, str) else int(mode)
         with torch.cuda.device(self.device):
             if isinstance(start, torch.Tensor):
@@ -421,12 +425,30 @@ class WalkEngine:
             if extend and thr is None and mode in (capi.MODE_SPARSE_OTF, capi.MODE_DENSE_OTF):
                 raise ValueError("extend=True needs set_thresholds() first")
             stream = torch.cuda.current_stream(self.device).cuda_stream
-            capi.check(self.lib.b2w_walk(self.handle, mode, float(p), float(q), int(bool(extend)), _ptr(thr),
-                                         _ptr(d_start), int(row0), n_rows, int(walk_length), int(seed) & (2 ** 64 - 1),
-                                         int(rng), _ptr(d_feed), _ptr(out), out.stride(0), _ptr(work), wb,
-                                         _ptr(stats_t), int(flags), C.c_void_p(stream)), "b2w_walk")
+            if mirrors:
+                if rng != capi.RNG_PHILOX:
+                    raise ValueError("mirrored walks run in the Philox regime only")
+                arr = (C.c_void_p * len(mirrors))(*[int(m) for m in mirrors])
+                capi.check(self.lib.b2w_walk_mirrored(self.handle, mode, float(p), float(q), int(bool(extend)), _ptr(thr),
+                                                      _ptr(d_start), int(row0), n_rows, int(walk_length),
+                                                      int(seed) & (2 ** 64 - 1), _ptr(out), out.stride(0), _ptr(work),
+                                                      wb, _ptr(stats_t), int(flags), C.c_void_p(stream), len(mirrors),
+                                                      arr), "b2w_walk_mirrored")
+            else:
+                capi.check(self.lib.b2w_walk(self.handle, mode, float(p), float(q), int(bool(extend)), _ptr(thr),
+                                             _ptr(d_start), int(row0), n_rows, int(walk_length), int(seed) & (2 ** 64 - 1),
+                                             int(rng), _ptr(d_feed), _ptr(out), out.stride(0), _ptr(work), wb,
+                                             _ptr(stats_t), int(flags), C.c_void_p(stream)), "b2w_walk")
             self.last_stats = stats_t
         return out[:n_rows]
+
+    def prepare(self, mode, p: float, q: float, extend: bool = False, flags: int = 0) -> str:
+        """Build whatever per-graph index ``walk`` would build for these parameters now (it is built on first use
+        otherwise) and return the name of the kernel that will serve them."""
+        m = MODES[mode] if isinstance(mode, str) else int(mode)
+        with torch.cuda.device(self.device):
+            self._maybe_edge_index(m, p, q, bool(extend), int(flags))
+        return self.kernel_name(m, p, q, extend, flags)
 
     def kernel_name(self, mode, p: float, q: float, extend: bool = False, flags: int = 0) -> str:
         mode = MODES[mode] if isinstance(mode, str) else int(mode)

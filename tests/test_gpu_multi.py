@@ -106,7 +106,7 @@ def _rank_main(rank, world, port, batches, gather, q):
     indptr, indices, data = _graph()
     eng = WalkEngine.from_csr(indptr, indices, data, device=dev)
     start = orc.shuffled_start(20000, 2, 5)[:33333]
-    if gather == "push" and ndev < world:
+    if gather in ("push", "mirror") and ndev < world:
         gather = "nccl"                                     # the peers' matrices are on the same device: nothing to map
     full = simulate_walks_distributed(eng, "SparseOTF", 4.0, 0.25, start, 30, seed=21, batches=batches, gather=gather)
     torch.cuda.synchronize()
@@ -116,7 +116,7 @@ def _rank_main(rank, world, port, batches, gather, q):
     eng.close()
 
 
-@pytest.mark.parametrize("batches,gather", [(1, "nccl"), (4, "nccl"), (3, "push")])
+@pytest.mark.parametrize("batches,gather", [(1, "nccl"), (4, "nccl"), (3, "push"), (1, "mirror"), (2, "mirror")])
 def test_two_ranks_cuda_walks_equal_single_rank(batches, gather):
     """CUDA kernels on two ranks (row0 offsets, batch-interleaved blocks, all-gather): every rank's matrix equals
     the one-rank matrix and the oracle."""
@@ -143,3 +143,35 @@ def test_two_ranks_cuda_walks_equal_single_rank(batches, gather):
     for rank, backend, kernel, full in res:
         assert kernel == "walk_uw_edge_kernel"
         assert np.array_equal(full, want), (rank, backend)
+
+
+@pytest.mark.parametrize("n_mirrors,row_off,L,pad", [(1, 0, 31, 0), (3, 5, 31, 0), (7, 2, 80, 0), (2, 1, 5, 0), (2, 3, 47, 3)])
+def test_mirrored_walk_writes_every_mirror(n_mirrors, row_off, L, pad):
+    """b2w_walk_mirrored (the all-gather fused into the kernel): the rows land, identical, in the local matrix and in
+    every mirror -- here other buffers of the same GPU stand in for the peers' matrices -- and nothing else of the
+    mirrors is touched.  Odd row lengths put the rows at all eight sector phases; `pad` widens the leading dimension."""
+    import torch
+    from pecanpy_b200.engine import WalkEngine
+    indptr, indices, data = _graph()
+    from oracle import oracle as orc
+    start = orc.shuffled_start(20000, 1, 9)[:7777]
+    eng = WalkEngine.from_csr(indptr, indices, data)
+    want = eng.walk("SparseOTF", 4.0, 0.25, start, L, seed=3, row0=row_off).cpu().numpy()
+    rows = start.size + row_off + 3
+    local = torch.full((rows, L + 2 + pad), -7, dtype=torch.int32, device=eng.device)
+    mirrors = [torch.full((rows, L + 2 + pad), -7, dtype=torch.int32, device=eng.device) for _ in range(n_mirrors)]
+    out = local[row_off:row_off + start.size, :L + 2]
+    ptrs = [m[row_off:].data_ptr() for m in mirrors]
+    eng.walk("SparseOTF", 4.0, 0.25, start, L, seed=3, row0=row_off, out=out, mirrors=ptrs)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), want)
+    for m in mirrors:
+        assert torch.equal(m, local)
+    assert int((local[:row_off] != -7).sum()) == 0 and int((local[row_off + start.size:] != -7).sum()) == 0
+    assert int((local[:, L + 2:] != -7).sum()) == 0
+    # kernels that do not mirror refuse instead of silently skipping the peers
+    with pytest.raises(Exception):
+        eng.walk("SparseOTF", 4.0, 0.25, start, L, seed=3, out=out, mirrors=ptrs, flags=0x40)   # B2W_FLAG_NO_EDGE_INDEX
+    with pytest.raises(Exception):
+        eng.walk("SparseOTF", 4.0, 0.25, start, L, seed=3, out=out, mirrors=[ptrs[0] + 4])       # not sector-congruent
+    eng.close()
