@@ -1,12 +1,9 @@
 #!/bin/bash
-# round 2, final validation on one B200: smoke(), full GPU suite, DRAM traffic of every workload's kernel, default bench,
+# round 2, final validation on one B200 (what the GPU budget had left: ~10 min): full GPU suite, default bench, smoke(),
 # launch list of the default bench, one full ncu capture of the headline kernel (full bench launch)
 mkdir -p gpurun_out
 P=gpurun_out/r2final
-python -c "import __graft_entry__ as g; g.smoke()" > ${P}_smoke.log 2>&1; tail -1 ${P}_smoke.log
-timeout 2400 python -m pytest tests -m gpu -q > ${P}_t_all.log 2>&1; echo "gpu suite: $(tail -1 ${P}_t_all.log)"
-bash tools/round2/collect_traffic.sh > ${P}_traffic.log 2>&1
-python tools/round2/make_traffic_json.py > ${P}_traffic_json.log 2>&1; cp profiles/traffic.json gpurun_out/traffic.json
+timeout 330 python -m pytest tests -m gpu -q > ${P}_t_all.log 2>&1; echo "gpu suite: $(tail -1 ${P}_t_all.log)"
 ( time python bench.py > ${P}_bench_default.json 2> ${P}_bench_default.err ) 2> ${P}_bench_time.txt; tail -3 ${P}_bench_time.txt
 python - <<'PY'
 import json
@@ -22,7 +19,7 @@ try:
 except Exception as e:
     print('bench FAILED', e); print(open('gpurun_out/r2final_bench_default.err').read()[-1500:])
 PY
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file ${P}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e --no-extra > ${P}_ncu_launches.log 2>&1
-timeout 600 ncu --set full --import-source on --clock-control none -c 1 -f -k regex:walk_uw_edge -o ${P}_uw_edge_pl_full python bench.py --steps 1 --warmup 0 --no-cpu --no-e2e --no-extra > ${P}_ncu_full.log 2>&1
-timeout 600 ncu --set full --import-source on --clock-control none -c 1 -f -k regex:walk_wedge -o ${P}_wedge_plw_nw1 python bench.py --workload powerlaw-1M-10M-sparseotf-weighted --steps 1 --warmup 0 --no-cpu --no-e2e --no-extra --num-walks 1 > ${P}_ncu_wedge.log 2>&1
+python -c "import __graft_entry__ as g; g.smoke()" > ${P}_smoke.log 2>&1; tail -1 ${P}_smoke.log
+timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file ${P}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e --no-extra > ${P}_ncu_launches.log 2>&1
+timeout 200 ncu --set full --import-source on --clock-control none -c 1 -f -k regex:walk_uw_edge -o ${P}_uw_edge_pl_full python bench.py --steps 1 --warmup 0 --no-cpu --no-e2e --no-extra > ${P}_ncu_full.log 2>&1
 ls -la gpurun_out | grep r2final
