@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, total_rows, batches, q):
+def _worker(rank, world, port, total_rows, batches, q, gather="nccl"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -35,15 +35,17 @@ def _worker(rank, world, port, total_rows, batches, q):
                          rng=orc.RNG_PHILOX, seed=11, row0=lo, nthreads=1)
         out_block[: hi - lo].copy_(torch.from_numpy(w.view(np.int32)))
 
-    full = sharded_walks(walk_block, total_rows, L + 2, "cpu", batches=batches)
+    full = sharded_walks(walk_block, total_rows, L + 2, "cpu", batches=batches, gather=gather)
     blocks, B = shard_rows(total_rows, world, rank, batches)
     q.put((rank, blocks, B, full.numpy().view(np.uint32).copy()))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("total_rows,batches", [(800, 1), (777, 1), (777, 3), (50, 4)])
-def test_sharded_walks_match_single_process(total_rows, batches):
+@pytest.mark.parametrize("total_rows,batches,gather", [(800, 1, "nccl"), (777, 1, "nccl"), (777, 3, "nccl"), (50, 4, "nccl"),
+                                                        (777, 2, "mirror"), (777, 2, "push")])
+def test_sharded_walks_match_single_process(total_rows, batches, gather):
+    # ("mirror" / "push" need peer-mapped device matrices: on host tensors they must fall back to the all-gather)
     from oracle import oracle as orc
     z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "hub400_sparseotf_n2v.npz"))
     want = orc.walk_csr("SparseOTF", z["indptr"], z["indices"], z["data"], 4, 0.25, z["start"][:total_rows], 12,
@@ -51,7 +53,7 @@ def test_sharded_walks_match_single_process(total_rows, batches):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, total_rows, batches, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, total_rows, batches, q, gather)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
