@@ -544,6 +544,36 @@ def run_workload(name, args, K, W, rank, world, local_rank, *, do_e2e=True, do_c
     return line
 
 
+def on_rank0_while_others_sleep(dist, rank, work, timeout_s=1800.0):
+    """Rank 0 runs ``work()``; the other ranks SLEEP ON THE CPU until it is done (a flag file on this node -- the job
+    is one node by contract), then everybody meets in a barrier.  Waiting inside the barrier instead would leave an NCCL
+    kernel spinning on every other GPU, and rank 0's own kernels on those GPUs (b2w_walk_multi drives all of them from
+    one process) would have to time-slice against it."""
+    import tempfile
+    import uuid
+    tok = [os.path.join(tempfile.gettempdir(), "b2w_bench_" + uuid.uuid4().hex) if rank == 0 else None]
+    dist.broadcast_object_list(tok, src=0)
+    err = None
+    if rank == 0:
+        try:
+            work()
+        except BaseException as exc:                        # let the others go before failing
+            err = exc
+        open(tok[0], "w").close()
+    else:
+        t_end = time.time() + timeout_s
+        while not os.path.exists(tok[0]) and time.time() < t_end:
+            time.sleep(0.005)
+    dist.barrier()
+    if rank == 0:
+        try:
+            os.remove(tok[0])
+        except OSError:
+            pass
+    if err is not None:
+        raise err
+
+
 def run_e2e(torch, dist, eng, g, wl, start, L, K, rank, world, local_rank, steps_job, args):
     """The call a user makes, host buffers in and out: b2w_walk_host on one GPU; with N > 1, b2w_walk_multi from
     rank 0's process over all N GPUs of the box (one host thread per GPU, one pinned host matrix) while the other
@@ -553,7 +583,8 @@ def run_e2e(torch, dist, eng, g, wl, start, L, K, rank, world, local_rank, steps
     reps = max(2, min(K, 3))
     dt = None
     api = "WalkEngine.walk_host -> b2w_walk_host (pinned host start[] in, pinned host walk matrix out)"
-    if rank == 0:
+    def rank0_work():
+        nonlocal reps, dt, api
         h_start = torch.from_numpy(start.view(np.int32).copy()).pin_memory()
         h_out = torch.empty((tot, ld), dtype=torch.int32).pin_memory()
         np_start = h_start.numpy().view(np.uint32)
@@ -598,8 +629,11 @@ def run_e2e(torch, dist, eng, g, wl, start, L, K, rank, world, local_rank, steps
             for e2 in engines[1:]:
                 e2.close()
         del h_out, h_start
-    if world > 1:
-        dist.barrier()
+
+    if world == 1:
+        rank0_work()
+    else:
+        on_rank0_while_others_sleep(dist, rank, rank0_work)
     if rank != 0:
         return None
     return {"value": steps_job * reps / dt, "unit": "steps/s", "h2d_bytes_per_step": int(4 * tot),

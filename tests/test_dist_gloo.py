@@ -88,3 +88,49 @@ def test_shard_rows_cover_everything():
                 spans = sorted(s for s in spans if s[1] > s[0])
                 for a, b2 in zip(spans, spans[1:]):
                     assert a[1] == b2[0]
+
+
+def _sleep_worker(rank, world, port, fail, q):
+    import sys
+    import time
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    done_at = [None]
+
+    def work():
+        time.sleep(0.5)
+        done_at[0] = time.time()
+        if fail:
+            raise RuntimeError("rank 0 failed")
+
+    raised = False
+    try:
+        bench.on_rank0_while_others_sleep(dist, rank, work)
+    except RuntimeError:
+        raised = True
+    q.put((rank, done_at[0], time.time(), raised))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail", [False, True])
+def test_bench_other_ranks_sleep_until_rank0_is_done(fail):
+    """bench.py's e2e leg at N > 1: rank 0 works, the others sleep on the CPU and leave only after it has finished;
+    a failure on rank 0 is raised there and does not strand the others."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sleep_worker, args=(r, 3, port, fail, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    t_done = res[0][1]
+    assert t_done is not None
+    for rank, _, left_at, raised in res:
+        assert left_at >= t_done
+        assert raised == (fail and rank == 0)
