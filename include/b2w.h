@@ -342,6 +342,14 @@ int b2w_push_rows(int device, void* const* d_peers, int n_peers, int self, uint6
 /* the same with one stream per peer (streams[p] for p != self): copies to different peers run concurrently */
 int b2w_push_rows_streams(int device, void* const* d_peers, int n_peers, int self, uint64_t row_lo, uint64_t rows,
                           uint64_t row_bytes, void* const* streams);
+/* SURVEY.md 8b's b2w_allgather_rows (the in-place all-gather that ends a multi-rank job; reference counterpart: none,
+ * pecanpy.py:182-206 fills one host matrix), without an NCCL dependency in this library: rank `self` owns rows
+ * [self * rows_per_rank, (self + 1) * rows_per_rank) of the [n_peers * rows_per_rank, row_len] u32 matrix and queues
+ * their copy into every peer's mapped matrix on `stream` (= b2w_push_rows of that block).  Complete on a rank after
+ * every rank has synchronised its stream (a host barrier).  Callers that hold an ncclComm_t can equally run
+ * ncclAllGather on the same buffers (pecanpy_b200/dist.py does, by default); b2w_walk_mirrored needs neither. */
+int b2w_allgather_rows(int device, void* const* d_peers, int n_peers, int self, uint64_t rows_per_rank,
+                       uint32_t row_len, void* stream);
 
 /* Sum of (effective_length - 1) over the rows of a device walk matrix (the metric's unit). */
 int b2w_count_steps(const uint32_t* d_out, uint64_t n_rows, uint32_t walk_length, uint64_t ld_out,

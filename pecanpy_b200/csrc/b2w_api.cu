@@ -361,7 +361,7 @@ static int walk_impl(const b2w_graph* g, int mode, double p, double q, int exten
   for (int k = 0; k < n_mirrors; ++k) P.mirror_delta[k] = (long long)(d_mirrors[k] - d_out);
   cudaStream_t s = (cudaStream_t)stream;
   if (n_mirrors) {
-    // only the kernel that writes its rows through RowWriter mirrors them (unweighted SparseOTF with the edge index)
+    // only the kernel that writes its rows through WarpRowTile mirrors them (unweighted SparseOTF with the edge index)
     const bool ok = warp_kernel && !ext && !(flags & B2W_FLAG_NO_UNWEIGHTED_KERNEL) && b2w_uw_eligible(g, p, q) &&
                     (g->flags & B2W_GRAPH_HAS_EDGE_INDEX) && !(flags & (B2W_FLAG_NO_EDGE_INDEX | B2W_FLAG_COOP)) && !((flags >> 8) & 0xFF);
     if (!ok) { b2w_set_error("b2w_walk_mirrored: this mode / graph is not served by a mirroring kernel (use b2w_walk + an all-gather)"); return B2W_ERR_UNSUPPORTED; }

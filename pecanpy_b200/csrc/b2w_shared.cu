@@ -1,12 +1,15 @@
-// b2w_shared.cu -- one-node all-gather of the walk matrix by the copy engines (no kernel, no SMs).
+// b2w_shared.cu -- walk matrices shared between the ranks of one node (CUDA IPC), and their all-gather by the copy
+// engines (no kernel, no SMs).
 //
 // Multi-process jobs (one rank per GPU) end with every rank holding the whole walk matrix.  The walk
-// kernels fill the chip, so a collective that runs its own kernels beside them (NCCL) takes SMs away: overlapping
-// an NCCL all-gather with the walk slowed the walk 2x.  Here every rank allocates its matrix through
+// kernels fill the chip, so a collective that runs its own kernels beside them (NCCL) takes SMs away and gains nothing
+// when overlapped with the walk.  Here every rank allocates its matrix through
 // b2w_shared_alloc (cudaMalloc + an IPC handle), maps the peers' matrices with b2w_shared_open (cudaIpcOpenMemHandle
 // from its OWN device: peer access over NVLink is enabled lazily, no context is created on the peer GPU), and after
 // each walked batch calls b2w_push_rows: one cudaMemcpyAsync per peer, device to device, on a local side stream --
 // DMA over NVLink while the next batch is being walked.  A barrier between the ranks ends the pass.
+// The same mapped matrices are what b2w_walk_mirrored (b2w_api.cu, b2w_rowout.cuh) stores into from inside the walk
+// kernel -- the variant that removes the gather altogether.
 #include <cstring>
 
 #include "b2w_common.cuh"
@@ -82,4 +85,10 @@ extern "C" int b2w_push_rows_streams(int device, void* const* d_peers, int n_pee
     B2W_CUDA(cudaMemcpyAsync(static_cast<char*>(d_peers[p]) + off, src, n, cudaMemcpyDeviceToDevice, (cudaStream_t)streams[p]));
   }
   return B2W_OK;
+}
+
+extern "C" int b2w_allgather_rows(int device, void* const* d_peers, int n_peers, int self, uint64_t rows_per_rank,
+                                  uint32_t row_len, void* stream) {
+  if (self < 0) { b2w_set_error("b2w_allgather_rows: bad argument"); return B2W_ERR_INVALID; }
+  return b2w_push_rows(device, d_peers, n_peers, self, (uint64_t)self * rows_per_rank, rows_per_rank, 4ull * row_len, stream);
 }

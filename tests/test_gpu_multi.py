@@ -175,3 +175,26 @@ def test_mirrored_walk_writes_every_mirror(n_mirrors, row_off, L, pad):
     with pytest.raises(Exception):
         eng.walk("SparseOTF", 4.0, 0.25, start, L, seed=3, out=out, mirrors=[ptrs[0] + 4])       # not sector-congruent
     eng.close()
+
+
+def test_allgather_rows_entry_point():
+    """b2w_allgather_rows (SURVEY 8b's name for the trailing all-gather; here copy engines over mapped matrices): each
+    of three `ranks` -- three matrices of one GPU stand in for the mapped peers -- pushes its own row block; afterwards
+    all matrices are equal and hold every block."""
+    import ctypes as C
+    import torch
+    from pecanpy_b200 import _capi as capi
+    lib = capi.lib()
+    world, R, ld = 3, 1000, 82
+    mats = [torch.zeros((world * R, ld), dtype=torch.int32, device="cuda:0") for _ in range(world)]
+    for r, m in enumerate(mats):
+        m[r * R:(r + 1) * R] = torch.randint(1, 1 << 30, (R, ld), dtype=torch.int32, device="cuda:0")
+    want = torch.cat([mats[r][r * R:(r + 1) * R] for r in range(world)])
+    peers = (C.c_void_p * world)(*[m.data_ptr() for m in mats])
+    st = torch.cuda.current_stream().cuda_stream
+    for r in range(world):
+        capi.check(lib.b2w_allgather_rows(0, peers, world, r, R, ld, C.c_void_p(st)), "b2w_allgather_rows")
+    torch.cuda.synchronize()
+    for m in mats:
+        assert torch.equal(m, want)
+    assert lib.b2w_allgather_rows(0, peers, world, world, R, ld, C.c_void_p(st)) != capi.OK     # self out of range
