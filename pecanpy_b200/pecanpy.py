@@ -10,7 +10,9 @@ the raw ``uint32[tot, L+2]`` matrix in the layout of ``Base._random_walks`` (pec
 What changes with respect to the reference:
 
 * the njit closure pair ``get_move_forward()`` / ``get_has_nbrs()`` cannot be called from a GPU;
-  the strategy is selected by the class (``_MODE``) instead;
+  the strategy is selected by the class (``_MODE``) instead.  ``_random_walks`` keeps the reference's positional
+  signature and ignores the two callbacks; ``get_has_nbrs()`` returns a plain host callable, ``get_move_forward()``
+  raises;
 * random numbers: Philox4x32-10 keyed by ``(random_state, global walker row, step)`` instead of a
   per-thread MT19937, so seeded walks are reproducible for ANY thread / GPU count (the reference
   is reproducible only at one thread, pecanpy.py:51-55).  The start-node shuffle stays on the host
@@ -133,6 +135,29 @@ class Base(BaseGraph):
             return walk_host_multi(self, start, walk_length, seed)
         return self.engine.walk_host(self._MODE, self.p, self.q, start, walk_length, seed, extend=bool(self.extend))
 
+    def _random_walks(self, tot_num_jobs: int, walk_length: int, random_state: Optional[int], start_node_idx_ary,
+                      has_nbrs=None, move_forward=None, progress_proxy=None) -> np.ndarray:
+        """The reference's kernel entry (pecanpy.py:164-210; a staticmethod there, called ``self._random_walks(...)``)
+        with its positional arguments and its return value: ``uint32[tot_num_jobs, walk_length + 2]``, row i = the
+        walk from ``start_node_idx_ary[i]``.  ``has_nbrs`` / ``move_forward`` (the njit strategy callbacks) are
+        accepted and ignored: the strategy is this class's mode, evaluated by the CUDA kernels.
+        ``random_state=None`` draws a fresh seed, like the reference's unseeded run."""
+        from .engine import new_seed
+        self._preprocess_transition_probs()
+        start = np.ascontiguousarray(np.asarray(start_node_idx_ary)[:tot_num_jobs], dtype=np.uint32)
+        if start.size != tot_num_jobs:
+            raise ValueError("start_node_idx_ary holds fewer than tot_num_jobs entries")
+        self.last_seed = new_seed() if random_state is None else int(random_state)
+        return self.engine.walk_host(self._MODE, self.p, self.q, start, walk_length, self.last_seed,
+                                     extend=bool(self.extend))
+
+    def get_move_forward(self):
+        """The reference returns an njit closure here (graph.py:103-105, pecanpy.py:384-440, 522-561, 576-614) that
+        ``_random_walks`` calls once per step.  A GPU kernel cannot call back into the host per step: the strategy
+        is the class (mode enum of include/b2w.h) and this seam does not exist."""
+        raise NotImplementedError("pecanpy_b200 evaluates the walk strategy inside its CUDA kernels; there is no per-step "
+                                  "move_forward callback -- call simulate_walks / simulate_walks_array / _random_walks")
+
     def _map_walk(self, walk_idx_ary) -> List[str]:
         end_idx = walk_idx_ary[-1]
         return [self.nodes[i] for i in walk_idx_ary[:end_idx]]
@@ -175,6 +200,15 @@ class _SparseBase(Base, SparseGraph):
     def _make_engine(self, device=None):
         from .engine import WalkEngine
         return WalkEngine.from_csr(self.indptr, self.indices, self.data, device=device or self.device)
+
+    def get_has_nbrs(self):
+        """Host callable with the meaning of rw/sparse_rw.py:12-20 (the kernels test the same thing themselves)."""
+        indptr = self.indptr
+
+        def has_nbrs(idx):
+            return bool(indptr[idx] != indptr[idx + 1])
+
+        return has_nbrs
 
 
 class SparseOTF(_SparseBase):
@@ -262,3 +296,12 @@ class DenseOTF(Base, DenseGraph):
     def _make_engine(self, device=None):
         from .engine import WalkEngine
         return WalkEngine.from_dense(self.data, self.nonzero, device=device or self.device)
+
+    def get_has_nbrs(self):
+        """Host callable with the meaning of rw/dense_rw.py:21-32."""
+        nonzero = self.nonzero
+
+        def has_nbrs(idx):
+            return bool(nonzero[idx].any())
+
+        return has_nbrs

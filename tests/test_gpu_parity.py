@@ -483,3 +483,23 @@ def test_dropin_rebuilds_device_copy_when_the_graph_changes(mods):
                         extend=True, thr=thr, rng=orc.RNG_PHILOX, seed=1)
     assert np.array_equal(m1, want) and not np.array_equal(t0, thr)
     g.release(); s.release()
+
+
+@pytest.mark.gpu
+def test_random_walks_entry_keeps_the_reference_signature():
+    """Base._random_walks(tot, L, random_state, start, has_nbrs, move_forward, progress) -- reference
+    pecanpy.py:164-210, the call SURVEY 8d times -- returns the matrix simulate_walks_array builds from the same start
+    array and seed; the two callbacks are accepted and ignored."""
+    from pecanpy_b200 import pecanpy as pp
+    from pecanpy_b200.synth import power_law_csr
+    indptr, indices, data = power_law_csr(3000, 30000, seed=4)
+    g = pp.SparseOTF(p=0.5, q=2, random_state=7)
+    g.indptr, g.indices, g.data = indptr, indices, data
+    g.set_node_ids(None, implicit_ids=True, num_nodes=3000)
+    want = g.simulate_walks_array(2, 20)
+    start = g._start_nodes(2)
+    got = g._random_walks(start.size, 20, 7, start, g.get_has_nbrs(), None, None)
+    assert got.dtype == np.uint32 and np.array_equal(got, want)
+    part = g._random_walks(100, 20, 7, start)                  # a prefix of the jobs: the same rows (Philox by row)
+    assert np.array_equal(part, want[:100])
+    g.release()

@@ -250,3 +250,17 @@ def test_native_parser_other_delimiter_errors_and_unicode_fallback(tmp_path):
         drop.write_text("a\tb\t-1\nb\tc\t2\n")
         names, src, dst, w = _parse_edge_list_native(str(drop), True, "\t")
     assert names == ["b", "c"] and len(rec) == 1 and "Non-positive" in str(rec[0].message)
+
+
+def test_strategy_seams_of_the_reference_api():
+    """get_has_nbrs() keeps the meaning of rw/sparse_rw.py:12-20 / rw/dense_rw.py:21-32 as a host callable;
+    get_move_forward() (an njit per-step callback in the reference) does not exist on a GPU and says so."""
+    from pecanpy_b200 import pecanpy as pp
+    adj = np.array([[0, 1, 0, 0], [1, 0, 2, 0], [0, 2, 0, 0], [0, 0, 0, 0]], dtype=float)
+    ids = ["a", "b", "c", "d"]
+    for cls in (pp.SparseOTF, pp.PreComp, pp.DenseOTF):
+        g = cls.from_mat(adj, ids, p=1, q=1)
+        has = g.get_has_nbrs()
+        assert [has(i) for i in range(4)] == [True, True, True, False]
+        with pytest.raises(NotImplementedError):
+            g.get_move_forward()
