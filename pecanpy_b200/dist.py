@@ -47,7 +47,11 @@ class PeerMatrix:
     ``push`` copies this rank's rows straight into the same rows of every peer's matrix with device-to-device DMA over
     NVLink (b2w_push_rows: plain cudaMemcpyAsync on a local side stream).  It runs no kernel, so it overlaps with a
     walk kernel that fills the chip without taking SMs from it.  ``finish`` waits for this rank's copies and for every
-    peer's (a barrier): then ``self.full`` holds all rows.  ``close`` unmaps and frees (collective)."""
+    peer's (a barrier): then ``self.full`` holds all rows.  ``close`` unmaps and frees (collective).
+
+    The same mapped matrices serve the FUSED gather: ``mirror_ptrs(row)`` are the addresses the walk kernel stores its
+    rows to itself (engine.walk(..., mirrors=...) -> b2w_walk_mirrored); ``finish`` is then just the barrier.
+    ``ok`` is False on every rank if any rank could not allocate or map (no peer access): fall back to NCCL."""
 
     def __init__(self, rows: int, row_len: int, device, group=None):
         import ctypes as C
@@ -61,24 +65,31 @@ class PeerMatrix:
         nbytes = max(1, rows * self.row_bytes)
         ptr = C.c_void_p(None)
         handle = C.create_string_buffer(64)
-        capi.check(self.lib.b2w_shared_alloc(self.device.index, nbytes, C.byref(ptr), handle), "b2w_shared_alloc")
-        self._ptr = ptr.value
+        self.ok, self.error = True, ""
+        self._ptr, self.full, self._mapped = None, None, [None] * self.world
+        # every step below is collective: a rank whose allocation or mapping fails keeps taking part and the ranks
+        # agree on `ok` at the end (a rank that raised here would leave the others waiting in a collective)
+        if self.lib.b2w_shared_alloc(self.device.index, nbytes, C.byref(ptr), handle) != capi.OK:
+            self.ok, self.error = False, self.lib.b2w_last_error().decode("utf-8", "replace")
+        else:
+            self._ptr = ptr.value
         with torch.cuda.device(self.device):
-            self.full = torch.as_tensor(_DevBuffer(self._ptr, (rows, row_len), self), device=self.device)
-            self.full.zero_()
-            torch.cuda.current_stream(self.device).synchronize()
+            if self._ptr is not None:
+                self.full = torch.as_tensor(_DevBuffer(self._ptr, (rows, row_len), self), device=self.device)
+                self.full.zero_()
+                torch.cuda.current_stream(self.device).synchronize()
             self.stream = torch.cuda.Stream(device=self.device)
             # one stream per peer: the copies to different peers run on different copy engines at the same time
             self.streams = [torch.cuda.Stream(device=self.device) if r != self.rank else self.stream
                             for r in range(self.world)]
             self._stream_ptrs = (C.c_void_p * self.world)(*[s.cuda_stream for s in self.streams])
         handles = [None] * self.world
-        dist.all_gather_object(handles, handle.raw, group=group)
-        self._mapped = [None] * self.world
-        self.ok, self.error = True, ""
+        dist.all_gather_object(handles, handle.raw if self._ptr is not None else None, group=group)
         for r, h in enumerate(handles):
             if r == self.rank:
                 self._mapped[r] = self._ptr
+            elif h is None or self._ptr is None:
+                self.ok = False
             else:
                 p = C.c_void_p(None)
                 if self.lib.b2w_shared_open(self.device.index, h, C.byref(p)) != capi.OK:
@@ -116,16 +127,18 @@ class PeerMatrix:
         torch.cuda.current_stream(self.device).synchronize()
 
     def close(self) -> None:
-        if self._ptr is None:
+        """Collective (also on a rank whose allocation failed): unmap, barrier, free."""
+        if self._mapped is None:
             return
         torch.cuda.synchronize(self.device)
         for r, p in enumerate(self._mapped):
             if r != self.rank and p:
                 self.capi.check(self.lib.b2w_shared_close(self.device.index, self.C.c_void_p(p)), "b2w_shared_close")
-        self._mapped = []
+        self._mapped = None
         dist.barrier(self.group)                               # nobody frees before everybody has unmapped
         self.full = None
-        self.capi.check(self.lib.b2w_shared_free(self.device.index, self.C.c_void_p(self._ptr)), "b2w_shared_free")
+        if self._ptr is not None:
+            self.capi.check(self.lib.b2w_shared_free(self.device.index, self.C.c_void_p(self._ptr)), "b2w_shared_free")
         self._ptr = None
 
 
