@@ -1,0 +1,122 @@
+"""Differential check of the CPU oracle against the UNMODIFIED reference on freshly drawn cases.
+
+TEST INFRASTRUCTURE (like everything under oracle/): run in the build container only -- the reference is a Python/Numba
+package under /root/reference that cannot travel to the GPU box.  ``python oracle/fuzz_reference.py --cases 12 --seed 0``
+draws random small graphs (weighted / unweighted, undirected / directed with dead ends, isolated nodes, hubs), random
+(p, q), mode, node2vec+ on/off and gamma, runs the reference through its own ``from_mat`` ->
+``preprocess_transition_probs`` -> ``_random_walks`` path at one Numba thread (oracle/gen_golden.py's driver) and
+requires the oracle, replaying the same MT19937 word stream, to return the same walk matrix, noise thresholds and alias
+tables BIT FOR BIT.  The committed fixtures under tests/golden pin a fixed set of cases; this pins cases nobody chose.
+Exit code 0 = all equal; prints one line per case and a JSON summary.
+"""
+import argparse
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+
+import numpy as np  # noqa: E402
+
+import gen_golden as gg  # noqa: E402  (imports the reference with the stubs, sets one Numba thread)
+from oracle import oracle as orc  # noqa: E402
+
+PQ = [0.25, 0.5, 1.0, 2.0, 4.0, 0.3, 0.7, 1.7, 3.0]
+MODES = ["SparseOTF", "SparseOTF", "PreComp", "DenseOTF", "FirstOrderUnweighted", "PreCompFirstOrder"]
+
+
+def draw_case(rng):
+    mode = MODES[int(rng.integers(len(MODES)))]
+    kind = int(rng.integers(4))
+    n = int(rng.integers(12, 90))
+    gseed = int(rng.integers(1 << 30))
+    if kind == 0:
+        mat = gg.sym_weighted_graph(n, int(rng.integers(2 * n, 8 * n)), gseed, weighted=True,
+                                    isolated=int(rng.integers(0, 3)))
+    elif kind == 1:
+        mat = gg.sym_weighted_graph(n, int(rng.integers(2 * n, 8 * n)), gseed, weighted=False)
+    elif kind == 2:
+        mat = gg.hub_graph(n + 40, gseed)
+    else:
+        mat = gg.directed_with_dead_ends(n + 10, int(rng.integers(3 * n, 9 * n)), gseed)
+    first_order = mode in ("FirstOrderUnweighted", "PreCompFirstOrder")
+    if mode == "FirstOrderUnweighted":
+        mat = (mat != 0).astype(np.float64)
+    p = 1.0 if first_order else PQ[int(rng.integers(len(PQ)))]
+    q = 1.0 if first_order else PQ[int(rng.integers(len(PQ)))]
+    # node2vec+ assumes an undirected graph in the dense implementation (rw/dense_rw.py:92-93)
+    extend = (not first_order) and kind != 3 and bool(rng.integers(2))
+    gamma = float([0.0, 0.25, 0.5, 1.0][int(rng.integers(4))]) if extend else 0.0
+    return dict(mode=mode, kind=kind, mat=mat, p=p, q=q, extend=extend, gamma=gamma, seed=int(rng.integers(1000)),
+                num_walks=int(rng.integers(1, 4)), walk_length=int(rng.integers(3, 25)))
+
+
+def check_case(c):
+    cls = getattr(gg.pecanpy, c["mode"])
+    ids = [str(i) for i in range(c["mat"].shape[0])]
+    g = cls.from_mat(c["mat"], ids, p=c["p"], q=c["q"], extend=c["extend"], gamma=c["gamma"], random_state=c["seed"])
+    start, want = gg.ref_walk_matrix(g, c["num_walks"], c["walk_length"])
+    L = c["walk_length"]
+    bad = []
+    if not np.array_equal(orc.shuffled_start(len(ids), c["num_walks"], c["seed"]), start):
+        bad.append("start array")
+    words = orc.mt_words(c["seed"], 64 + 6 * start.size * L)
+    thr = None
+    if c["mode"] == "DenseOTF":
+        data, nz = np.asarray(g.data), np.asarray(g.nonzero)
+        if c["extend"]:
+            thr = orc.noise_thresholds_dense(data, nz.astype(bool), c["gamma"])
+            if not np.array_equal(thr.view(np.uint32), g.get_noise_thresholds().view(np.uint32)):
+                bad.append("thresholds")
+        got = orc.walk_dense(data, nz, c["p"], c["q"], start, L, extend=c["extend"], thr=thr, rng=orc.RNG_WORDS,
+                             words=words)
+    else:
+        if c["extend"]:
+            thr = orc.noise_thresholds_csr(g.indptr, g.data, c["gamma"])
+            if not np.array_equal(thr.view(np.uint32), g.get_noise_thresholds().view(np.uint32)):
+                bad.append("thresholds")
+        alias = None
+        if c["mode"] == "PreComp":
+            aip, j, q = orc.alias_build(g.indptr, g.indices, g.data, c["p"], c["q"], c["extend"], thr)
+            if not (np.array_equal(aip, g.alias_indptr) and np.array_equal(j, g.alias_j)
+                    and np.array_equal(q.view(np.uint32), g.alias_q.view(np.uint32))):
+                bad.append("alias tables")
+            alias = (aip, j, q)
+        elif c["mode"] == "PreCompFirstOrder":
+            j, q = orc.alias_build_first_order(g.indptr, g.indices, g.data)
+            if not (np.array_equal(j, g.alias_j) and np.array_equal(q.view(np.uint32), g.alias_q.view(np.uint32))):
+                bad.append("alias tables")
+            alias = (None, j, q)
+        got = orc.walk_csr(c["mode"], g.indptr, g.indices, g.data, c["p"], c["q"], start, L, alias=alias,
+                           extend=c["extend"], thr=thr, rng=orc.RNG_WORDS, words=words)
+    if got.shape != want.shape or not np.array_equal(got, want):
+        bad.append("walk matrix")
+    steps = int((want[:, -1].astype(np.int64) - 1).sum())
+    dead = int((want[:, -1] != L + 1).sum())
+    return bad, steps, dead
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", type=int, default=12)
+    ap.add_argument("--seed", type=int, default=0)
+    args = ap.parse_args()
+    rng = np.random.default_rng(args.seed)
+    failures, steps_total = [], 0
+    for k in range(args.cases):
+        c = draw_case(rng)
+        bad, steps, dead = check_case(c)
+        steps_total += steps
+        tag = (f"{c['mode']} kind={c['kind']} n={c['mat'].shape[0]} p={c['p']} q={c['q']} extend={c['extend']} "
+               f"gamma={c['gamma']} seed={c['seed']} walks={c['num_walks']}x{c['walk_length']} steps={steps} "
+               f"truncated_rows={dead}")
+        print(("MISMATCH " + ", ".join(bad) + ": " if bad else "ok: ") + tag, flush=True)
+        if bad:
+            failures.append(tag)
+    print(json.dumps({"cases": args.cases, "seed": args.seed, "steps": steps_total, "failures": failures}))
+    return 1 if failures else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

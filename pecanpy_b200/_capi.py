@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("B2W_LIBRARY") or os.path.join(_HERE, "lib", "libb2w.s
 
 OK = 0
 ERR_UNSUPPORTED = -4
+ERR_NOMEM = -5
 MODE_SPARSE_OTF, MODE_PRECOMP, MODE_DENSE_OTF, MODE_FIRST_ORDER_UNWEIGHTED, MODE_PRECOMP_FIRST_ORDER = range(5)
 RNG_PHILOX, RNG_FEED = 0, 1
 FLAG_FORCE_EXACT_REPLAY = 0x1

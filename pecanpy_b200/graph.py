@@ -83,8 +83,10 @@ def _parse_edge_list_native(path: str, weighted: bool, delimiter: str):
                                 C.byref(n), C.byref(nb), C.byref(nd))
     if rc == capi.ERR_UNSUPPORTED:
         return None                       # non-ASCII file: Python's Unicode-aware strip() decides
+    if rc == capi.ERR_NOMEM:
+        raise MemoryError(lib.b2w_last_error().decode("utf-8", "replace"))
     if rc != capi.OK:
-        raise ValueError(lib.b2w_last_error().decode("utf-8", "replace"))
+        return None                       # a malformed line: the Python parser raises the reference's own exception
     try:
         src = np.empty(m.value, dtype=np.uint32)
         dst = np.empty(m.value, dtype=np.uint32)
@@ -113,20 +115,24 @@ def _parse_edge_list_native(path: str, weighted: bool, delimiter: str):
 def _parse_edge_list_python(path: str, weighted: bool, delimiter: str = "\t"):
     """The same parse in NumPy-vectorised Python (Unicode aware; used when the native parser is unavailable)."""
     with open(path, encoding="utf-8") as f:                 # universal newlines, as the reference's `for line in f`
-        lines = f.read().split("\n")                        # (str.splitlines would also break at \x0b, \x1c, \x85, ...)
+        pieces = f.read().split("\n")                       # (str.splitlines would also break at \x0b, \x1c, \x85, ...)
+    # the lines as the reference's loop sees them (each with its "\n", except an unterminated last one);
     # blank lines are skipped (the reference raises IndexError on them, graph.py:166-167: a documented tolerance)
+    lines = [ln + "\n" for ln in pieces[:-1]] + ([pieces[-1]] if pieces[-1] else [])
     lines = [ln for ln in lines if ln.strip()]
     if not lines:
         return [], np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros(0, np.float64)
     parts = [ln.strip().split(delimiter) for ln in lines]
-    if weighted:
-        for ln, t in zip(lines, parts):
+    wl = []
+    for ln, t in zip(lines, parts):                         # errors in file order, of the reference's classes and texts
+        if len(t) < 2:
+            raise IndexError("list index out of range")     # terms[1] (graph.py:168)
+        if weighted:
             if len(t) != 3:
                 raise ValueError(f"Expecting three columns in the edge list file for a weighted graph, "
                                  f"got {len(t)} instead: {ln!r}")
-        w = np.array([float(t[-1]) for t in parts], dtype=np.float64)
-    else:
-        w = np.ones(len(parts), dtype=np.float64)
+            wl.append(float(t[-1]))
+    w = np.array(wl, dtype=np.float64) if weighted else np.ones(len(parts), dtype=np.float64)
     a = np.array([t[0].strip() for t in parts], dtype=object)
     b = np.array([t[1].strip() for t in parts], dtype=object)
     bad = w <= 0

@@ -228,16 +228,19 @@ def test_native_parser_other_delimiter_errors_and_unicode_fallback(tmp_path):
     nat = _parse_edge_list_native(str(p), True, ",")
     assert _same_parse(nat, _reference_read_lines(str(p), True, ","))
     assert nat[0] == ["a", "b", "c"]
+    # malformed lines: the native parser steps aside and the Python parser raises what the reference raises
+    # (graph.py:166-178: IndexError from terms[1], ValueError for the column count with the line's repr, float()'s own)
     bad = tmp_path / "bad.edg"
-    bad.write_text("a\tb\n")
-    with pytest.raises(ValueError, match="three columns"):
-        _parse_edge_list_native(str(bad), True, "\t")
-    bad.write_text("a\tb\tx1\n")
-    with pytest.raises(ValueError, match="float"):
-        _parse_edge_list_native(str(bad), True, "\t")
-    bad.write_text("lonely\n")
-    with pytest.raises(ValueError):
-        _parse_edge_list_native(str(bad), False, "\t")
+    for text, weighted, exc, match in [("a\tb\n", True, ValueError, r"got 2 instead: 'a\\tb\\n'"),
+                                       ("a\tb\tx1\n", True, ValueError, "could not convert string to float: 'x1'"),
+                                       ("a\tb\nlonely\n", False, IndexError, "list index out of range"),
+                                       ("a\tb\t1\t2", True, ValueError, r"got 4 instead: 'a\\tb\\t1\\t2'")]:
+        bad.write_text(text)
+        assert _parse_edge_list_native(str(bad), weighted, "\t") is None
+        with pytest.raises(exc, match=match):
+            SparseGraph().read_edg(str(bad), weighted=weighted, directed=False)
+        with pytest.raises(exc, match=match):
+            _parse_edge_list_python(str(bad), weighted, "\t")
     uni = tmp_path / "u.edg"
     uni.write_text("café\tnaïve\n x \tcafé\n", encoding="utf-8")
     assert _parse_edge_list_native(str(uni), False, "\t") is None      # refused: Python's strip() is Unicode aware
