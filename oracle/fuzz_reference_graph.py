@@ -115,8 +115,20 @@ def check(text, weighted, directed, delim, path):
             return csr_of(g)
         return run
 
+    def dense_of(mod):
+        def run():
+            g = mod.DenseGraph()
+            g.read_edg(path, weighted, directed, delim)
+            return list(g.nodes), np.asarray(g.data), np.asarray(g.nonzero)
+        return run
+
     want, werr, wmsg = read_with(ref)
     bad = []
+    if not werr:                                           # DenseGraph.read_edg (graph.py:613-625: read + to_dense)
+        dw, _, _ = read_with(dense_of(ref_graph))
+        dg, derr, _ = read_with(dense_of(our_graph))
+        if derr or not same(dg, dw):
+            bad.append(f"DenseGraph.read_edg differs ({derr})")
     for label, fn in (("read_edg", ours(False)), ("python parser", ours(True))):
         got, gerr, gmsg = read_with(fn)
         if werr or gerr:
