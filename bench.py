@@ -7,9 +7,11 @@ One "step" = one pass of the hot path (Base._random_walks, reference pecanpy.py:
 whole job: num_walks x num_nodes walkers x walk_length steps.  Default workload = BASELINE config #3
 (the configuration the north-star target is quoted on): synthetic power-law graph, 1M nodes / 10M
 edges, SparseOTF p=4 q=0.25, 10 x 80.  With N > 1 (torchrun, one rank per GPU) the graph is replicated,
-the shuffled start array is sharded over the ranks and every rank ends with the whole walk matrix:
-the rows are walked in a few batches and each batch is all-gathered (NCCL over NVLink) while the next one
-is being walked ("scaling": "strong": the job is fixed).
+the shuffled start array is sharded over the ranks and every rank ends with the whole walk matrix
+("scaling": "strong": the job is fixed).  How the matrix gets everywhere is --gather: `mirror` = the walk kernel
+stores its rows into every peer's CUDA-IPC-mapped matrix itself, over NVLink, while it walks (b2w_walk_mirrored; no
+gather phase), `nccl` = one all-gather after the walk (or per batch with --batches), `push` = copy engines; `auto`
+(default) = mirror where the kernel supports it, chosen against NCCL by a warm-up probe beyond 4 GPUs.
 
 Prints ONE JSON line (rank 0).  `value` = steps of the whole job / device time (max over ranks),
 inputs resident in HBM.  `e2e` = the same through the host-buffer C-ABI call (b2w_walk_host; at N > 1

@@ -26,10 +26,12 @@ PQ = [0.25, 0.5, 1.0, 2.0, 4.0, 0.3, 0.7, 1.7, 3.0]
 MODES = ["SparseOTF", "SparseOTF", "PreComp", "DenseOTF", "FirstOrderUnweighted", "PreCompFirstOrder"]
 
 
-def draw_case(rng):
+def draw_case(rng, big=False):
     mode = MODES[int(rng.integers(len(MODES)))]
     kind = int(rng.integers(4))
     n = int(rng.integers(12, 90))
+    if big:                                                # hub rows of several hundred entries: where the order of the
+        kind, n = 2, int(rng.integers(400, 1500))          # f32 additions decides the draw (and choice == deg happens)
     gseed = int(rng.integers(1 << 30))
     if kind == 0:
         mat = gg.sym_weighted_graph(n, int(rng.integers(2 * n, 8 * n)), gseed, weighted=True,
@@ -101,11 +103,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=12)
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--big", action="store_true", help="power-law graphs with hub rows of several hundred entries")
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
     failures, steps_total = [], 0
     for k in range(args.cases):
-        c = draw_case(rng)
+        c = draw_case(rng, args.big)
         bad, steps, dead = check_case(c)
         steps_total += steps
         tag = (f"{c['mode']} kind={c['kind']} n={c['mat'].shape[0]} p={c['p']} q={c['q']} extend={c['extend']} "
