@@ -283,7 +283,8 @@ int b2w_walk(const b2w_graph* g, int mode, double p, double q, int extend, const
              uint64_t seed, int rng_mode, const double* d_feed, uint32_t* d_out, uint64_t ld_out,
              void* d_work, size_t work_bytes, b2w_walk_stats* d_stats, uint32_t flags, void* stream);
 
-/* b2w_walk with the all-gather FUSED into the kernel (multi-process jobs on one node): every row the kernel writes to
+/* b2w_walk (reference: Base._random_walks, pecanpy.py:164-210; the reference has no multi-GPU path) with the
+ * all-gather FUSED into the kernel (multi-process jobs on one node): every row the kernel writes to
  * d_out is also stored, sector by sector as it is produced, at the same place of up to 7 other matrices --
  * d_mirrors[k] = the address in peer k's matrix that corresponds to d_out (mapped with b2w_shared_open; congruent to
  * d_out modulo 32 bytes).  The stores travel over NVLink while the walk goes on; when the kernel has finished on every
