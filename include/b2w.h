@@ -322,6 +322,16 @@ int b2w_walk_multi(int n_graphs, b2w_graph* const* graphs, int mode, double p, d
                    const float* const* d_thr, const uint32_t* h_start, uint64_t n_rows, uint32_t walk_length,
                    uint64_t seed, uint32_t* h_out, uint64_t batch_rows, b2w_walk_stats* h_stats, uint32_t flags);
 
+/* ---- the start array of Base.simulate_walks (reference pecanpy.py:135-141), host side ---------------------
+ * h_start[num_nodes * num_walks] = num_walks copies of 0 .. num_nodes-1, shuffled exactly as
+ *     np.random.seed(random_state); np.random.shuffle(start)
+ * does (NumPy's legacy generator: Fisher-Yates from the top, partner by masked rejection on 32-bit MT19937 words) --
+ * the shuffle fixes the row order of the walk matrix.  mt_key[624] / *mt_pos = the state of NumPy's global generator
+ * after the caller has seeded it the reference's way (np.random.get_state()); on return they hold the state after the
+ * shuffle (store it back with np.random.set_state).  Several times faster than NumPy at 10^7 walkers (the partners
+ * are drawn ahead of the swaps and prefetched).  Plain host code: no device, no handle. */
+int b2w_shuffled_start(uint32_t num_nodes, uint32_t num_walks, uint32_t* mt_key, int32_t* mt_pos, uint32_t* h_start);
+
 /* ---- one-node all-gather by the copy engines (multi-process jobs, one rank per GPU) ----------------------
  * Replaces the trailing ncclAllGather of SURVEY.md 8b/8e where it has to OVERLAP with the walk: the walk kernels fill
  * the chip, a collective that runs kernels beside them slows them down; device-to-device DMA does not.

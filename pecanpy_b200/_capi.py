@@ -45,7 +45,7 @@ EXPORTS = [
     "b2w_edge_ckpt_work_bytes", "b2w_edge_ckpt_prepare", "b2w_edge_ckpt_finish", "b2w_graph_clear_edge_ckpt",
     "b2w_windex_work_bytes", "b2w_windex_prepare", "b2w_windex_finish", "b2w_graph_clear_windex",
     "b2w_shared_alloc", "b2w_shared_free", "b2w_shared_open", "b2w_shared_close", "b2w_push_rows", "b2w_push_rows_streams",
-    "b2w_walk_multi", "b2w_walk_mirrored", "b2w_allgather_rows", "b2w_alias_build_packed", "b2w_graph_set_alias_packed",
+    "b2w_walk_multi", "b2w_walk_mirrored", "b2w_allgather_rows", "b2w_shuffled_start", "b2w_alias_build_packed", "b2w_graph_set_alias_packed",
     "b2w_edge_index_work_bytes", "b2w_edge_index_prepare", "b2w_edge_index_finish", "b2w_graph_set_edge_index",
 ]
 
@@ -117,6 +117,7 @@ def lib():
     L.b2w_push_rows.argtypes = [i32, C.POINTER(vp), i32, i32, u64, u64, u64, vp]
     L.b2w_push_rows_streams.argtypes = [i32, C.POINTER(vp), i32, i32, u64, u64, u64, C.POINTER(vp)]
     L.b2w_allgather_rows.argtypes = [i32, C.POINTER(vp), i32, i32, u64, u32, vp]
+    L.b2w_shuffled_start.argtypes = [u32, u32, vp, C.POINTER(C.c_int32), vp]
     L.b2w_walk_kernel_name.argtypes = [vp, i32, dbl, dbl, i32, u32]
     L.b2w_walk_kernel_name.restype = C.c_char_p
     L.b2w_noise_thresholds.argtypes = [vp, dbl, vp, vp]

@@ -18,7 +18,7 @@ LIB = os.path.join(LIB_DIR, "libb2w.so")
 OBJ_DIR = os.path.join(os.path.dirname(HERE), "build", "obj")
 
 SOURCES = ["b2w_api.cu", "b2w_alias.cu", "b2w_dense.cu", "b2w_walk_thread.cu", "b2w_walk_warp.cu", "b2w_walk_uw.cu",
-           "b2w_thresholds.cu", "b2w_csr_build.cu", "b2w_edgelist.cu", "b2w_edge_index.cu", "b2w_walk_edge.cu", "b2w_shared.cu", "b2w_wedge.cu"]
+           "b2w_thresholds.cu", "b2w_csr_build.cu", "b2w_edgelist.cu", "b2w_edge_index.cu", "b2w_walk_edge.cu", "b2w_shared.cu", "b2w_wedge.cu", "b2w_start.cu"]
 # -fmad=false: the reference rounds every multiply and add separately (no FMA contraction);
 # no fast-math: IEEE division and no flush-to-zero are part of the bit-exactness contract.
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",

@@ -28,6 +28,37 @@ import numpy as np
 from .graph import BaseGraph, DenseGraph, SparseGraph
 
 
+def shuffled_start(num_nodes: int, num_walks: int, random_state) -> np.ndarray:
+    """The start array of pecanpy.py:135-141 -- ``num_walks`` copies of every node index, shuffled by NumPy's legacy
+    GLOBAL generator seeded with ``random_state`` -- bit for bit, including the state the global generator is left in.
+    NumPy seeds (so every seed type, ``None`` included, means what it means in the reference); the Fisher-Yates loop
+    itself runs natively (``b2w_shuffled_start``: 3-6x faster at 10^7 walkers, where NumPy's shuffle would cost several
+    times the GPU's whole walk).  Plain NumPy when the library is not built or the array has 2^32 entries or more."""
+    np.random.seed(random_state)
+    tot = int(num_nodes) * int(num_walks)
+    lib = None
+    if 2 <= tot < 2 ** 32:
+        try:
+            from . import _capi as capi
+            lib = capi.lib()
+        except (ImportError, OSError):
+            lib = None
+    if lib is None:
+        nodes = np.arange(num_nodes, dtype=np.uint32)                 # == np.array(range(n), dtype=np.uint32)
+        start = np.concatenate([nodes] * num_walks) if num_walks else np.zeros(0, np.uint32)
+        np.random.shuffle(start)
+        return start
+    import ctypes as C
+    name, key, pos, has_gauss, cached = np.random.get_state()
+    key = np.ascontiguousarray(key, dtype=np.uint32).copy()
+    cpos = C.c_int32(int(pos))
+    start = np.empty(tot, dtype=np.uint32)
+    capi.check(lib.b2w_shuffled_start(int(num_nodes), int(num_walks), C.c_void_p(key.ctypes.data), C.byref(cpos),
+                                      C.c_void_p(start.ctypes.data)), "b2w_shuffled_start")
+    np.random.set_state((name, key, int(cpos.value), has_gauss, cached))
+    return start
+
+
 class Base(BaseGraph):
     _MODE = ""
 
@@ -110,12 +141,7 @@ class Base(BaseGraph):
             self._preprocess_key = key
 
     def _start_nodes(self, num_walks: int) -> np.ndarray:
-        # pecanpy.py:135-141, verbatim semantics: NumPy legacy global generator
-        nodes = np.arange(self.num_nodes, dtype=np.uint32)            # == np.array(range(n), dtype=np.uint32)
-        start = np.concatenate([nodes] * num_walks)
-        np.random.seed(self.random_state)
-        np.random.shuffle(start)
-        return start
+        return shuffled_start(self.num_nodes, num_walks, self.random_state)
 
     def _seed(self) -> int:
         from .engine import new_seed
