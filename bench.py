@@ -338,9 +338,10 @@ def run_workload(name, args, K, W, rank, world, local_rank, *, do_e2e=True, do_c
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > L2 (126 MB)
     comm = torch.cuda.Stream(device=dev) if world > 1 else None
     def one_pass(seed, events=None):
-        """Walk this rank's blocks.  N > 1: each walked batch leaves for the other ranks while the next one is being
-        walked -- pushed into the peers' matrices by the copy engines (CUDA IPC + DMA over NVLink), or, with
-        --gather nccl, all-gathered by NCCL on a side stream."""
+        """Walk this rank's blocks.  N > 1, by `gather`: "mirror" -- the walk kernel itself stores the rows into every
+        peer's mapped matrix (nothing to do afterwards but the barrier in peer.finish); "push" -- each walked batch is
+        copied into the peers' matrices by the copy engines while the next one is walked; "nccl" -- all-gathered by
+        NCCL on a side stream."""
         cur = torch.cuda.current_stream(dev)
         for b, (r0, rows) in enumerate(blocks):
             if rows:
