@@ -122,8 +122,34 @@ def check(text, weighted, directed, delim, path):
             return list(g.nodes), np.asarray(g.data), np.asarray(g.nonzero)
         return run
 
+    def npz_and_mat(mod, src_mod):
+        """save (written by src_mod) -> read_npz (by mod), weighted and not; from_mat of the dense matrix."""
+        def run():
+            g0 = src_mod.SparseGraph()
+            g0.read_edg(path, weighted, directed, delim)
+            npz = path + "." + src_mod.__name__.split(".")[0] + ".npz"
+            g0.save(npz)
+            out = []
+            for wflag in (True, False):
+                g = mod.SparseGraph()
+                g.read_npz(npz, wflag)
+                out.append(([str(x) for x in g.nodes], np.asarray(g.indptr), np.asarray(g.indices), np.asarray(g.data)))
+            d = src_mod.DenseGraph()
+            d.read_edg(path, weighted, directed, delim)
+            g = mod.SparseGraph.from_mat(np.asarray(d.data), list(d.nodes))
+            out.append((list(g.nodes), np.asarray(g.indptr), np.asarray(g.indices), np.asarray(g.data)))
+            return out
+        return run
+
     want, werr, wmsg = read_with(ref)
     bad = []
+    if not werr and want[1].size > 1:                      # .npz round trips (graph.py:447-497) and from_mat (:513-528)
+        rr, _, _ = read_with(npz_and_mat(ref_graph, ref_graph))
+        for label, m, src in (("read_npz of a reference file / from_mat", our_graph, ref_graph),
+                              ("reference read_npz of this repo's file", ref_graph, our_graph)):
+            oo, oerr, _ = read_with(npz_and_mat(m, src))
+            if oerr or rr is None or any(not same(a, b) for a, b in zip(oo, rr)):
+                bad.append(f"{label} differs ({oerr})")
     if not werr:                                           # DenseGraph.read_edg (graph.py:613-625: read + to_dense)
         dw, _, _ = read_with(dense_of(ref_graph))
         dg, derr, _ = read_with(dense_of(our_graph))
