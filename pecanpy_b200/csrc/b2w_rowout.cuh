@@ -8,7 +8,12 @@
 // the row, so any row length / leading dimension works (rows of L + 2 = 82 words start at four different phases);
 // the head of the row before its first sector boundary and the tail after the last one are written word by word.
 #pragma once
+#ifdef B2W_HOST_TEST
+// g++ build for tests/test_rowtile_host.py (no GPU needed): tests/rowtile_harness.cpp supplies WalkParams, threadIdx,
+// uint4, __stcs and __syncwarp and runs the 32 lanes of a warp one after the other
+#else
 #include "b2w_common.cuh"
+#endif
 
 template <int THREADS>
 struct RowWriter {
