@@ -106,10 +106,21 @@ def main():
     ap.add_argument("--big", action="store_true", help="power-law graphs with hub rows of several hundred entries")
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
-    failures, steps_total = [], 0
+    failures, steps_total, skipped = [], 0, 0
     for k in range(args.cases):
         c = draw_case(rng, args.big)
-        bad, steps, dead = check_case(c)
+        try:
+            bad, steps, dead = check_case(c)
+        except ValueError as exc:
+            # the REFERENCE can crash: PreComp on a directed graph whose walker arrives at the last node over an edge
+            # that has no reverse edge slices its alias tables past their end and calls randint(0) (pecanpy.py:429-438
+            # after the "Neighbor not found" print) -- there is no reference result to compare with
+            if "empty range" not in str(exc):
+                raise
+            print(f"skipped (the reference raised {type(exc).__name__}: {exc}): {c['mode']} kind={c['kind']} "
+                  f"n={c['mat'].shape[0]} seed={c['seed']}", flush=True)
+            skipped += 1
+            continue
         steps_total += steps
         tag = (f"{c['mode']} kind={c['kind']} n={c['mat'].shape[0]} p={c['p']} q={c['q']} extend={c['extend']} "
                f"gamma={c['gamma']} seed={c['seed']} walks={c['num_walks']}x{c['walk_length']} steps={steps} "
@@ -117,7 +128,8 @@ def main():
         print(("MISMATCH " + ", ".join(bad) + ": " if bad else "ok: ") + tag, flush=True)
         if bad:
             failures.append(tag)
-    print(json.dumps({"cases": args.cases, "seed": args.seed, "steps": steps_total, "failures": failures}))
+    print(json.dumps({"cases": args.cases, "seed": args.seed, "steps": steps_total, "skipped": skipped,
+                      "failures": failures}))
     return 1 if failures else 0
 
 
