@@ -83,7 +83,9 @@ def read_with(fn):
 
 
 def csr_of(g):
-    return list(g.nodes), np.asarray(g.indptr), np.asarray(g.indices), np.asarray(g.data)
+    # (num_nodes / num_edges / density, graph.py:38-53, 416-421, ride along as a 3-vector)
+    props = np.array([g.num_nodes, g.num_edges, g.density], dtype=np.float64)
+    return list(g.nodes), np.asarray(g.indptr), np.asarray(g.indices), np.asarray(g.data), props
 
 
 def same(a, b):
@@ -119,7 +121,8 @@ def check(text, weighted, directed, delim, path):
         def run():
             g = mod.DenseGraph()
             g.read_edg(path, weighted, directed, delim)
-            return list(g.nodes), np.asarray(g.data), np.asarray(g.nonzero)
+            return (list(g.nodes), np.asarray(g.data), np.asarray(g.nonzero),
+                    np.array([g.num_nodes, g.num_edges, g.density], dtype=np.float64))
         return run
 
     def npz_and_mat(mod, src_mod):

@@ -192,7 +192,7 @@ class SparseGraph(BaseGraph):
     def num_edges(self) -> int:
         if self.indptr is None:
             raise ValueError("Empty graph.")
-        return int(self.indptr[-1])
+        return self.indptr[-1]                 # (a NumPy scalar, as in the reference, graph.py:416-421)
 
     def read_edg(self, path: str, weighted: bool, directed: bool, delimiter: str = "\t", device=None):
         """Load an edge list (reference graph.py:447-486).  With ``device`` (e.g. ``"cuda:0"``) the CSR is built on
@@ -252,7 +252,7 @@ class DenseGraph(BaseGraph):
     def num_edges(self) -> int:
         if self._nonzero is None:
             raise ValueError("Empty graph.")
-        return int(self._nonzero.sum())
+        return self._nonzero.sum()             # (a NumPy scalar, as in the reference, graph.py:563-569)
 
     @property
     def data(self):
