@@ -144,8 +144,50 @@ def check(text, weighted, directed, delim, path):
             return out
         return run
 
+    def adjlst(mod):
+        """AdjlstGraph (graph.py:108-387): read, the stored edges, the insertion counter, both conversions, save,
+        from_mat on the dense matrix (negative entries kept), from_adjlst_graph of both graph classes."""
+        def run():
+            g = mod.AdjlstGraph()
+            g.read(path, weighted, directed, delim)
+            out_path = path + "." + mod.__name__.split(".")[0] + ".saved"
+            mod.AdjlstGraph.save(g, out_path, not weighted, delim)
+            with open(out_path, encoding="utf-8") as f:
+                saved = f.read()
+            dense = g.to_dense()
+            signed = dense.copy()
+            signed[::2] *= -1.0
+            g2 = mod.AdjlstGraph.from_mat(signed, list(g.nodes))
+            sp = mod.SparseGraph.from_adjlst_graph(g)
+            dn = mod.DenseGraph.from_adjlst_graph(g)
+            return (list(g.nodes), [tuple(map(float, e)) for e in g.edges], int(g.num_edges), saved, g.to_csr(), dense,
+                    [tuple(map(float, e)) for e in g2.edges], int(g2.num_edges), g2.to_csr(),
+                    (list(sp.nodes), sp.indptr, sp.indices, sp.data), (list(dn.nodes), np.asarray(dn.data), np.asarray(dn.nonzero)))
+        return run
+
+    def deep_same(a, b):
+        if isinstance(a, (tuple, list)) and isinstance(b, (tuple, list)):
+            return len(a) == len(b) and all(deep_same(x, y) for x, y in zip(a, b))
+        if isinstance(a, np.ndarray) or isinstance(b, np.ndarray):
+            a, b = np.asarray(a), np.asarray(b)
+            return a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a.view(np.uint8), b.view(np.uint8))
+        return a == b and type(a) is type(b)
+
+    def all_warnings(fn):
+        with warnings.catch_warnings(record=True) as rec:
+            warnings.simplefilter("always")
+            try:
+                out, err = fn(), None
+            except Exception as exc:                       # noqa: BLE001
+                out, err = None, f"{type(exc).__name__}: {exc}"
+        return out, err, [str(r.message) for r in rec]
+
     want, werr, wmsg = read_with(ref)
     bad = []
+    ra, raerr, rawarn = all_warnings(adjlst(ref_graph))
+    oa, oaerr, oawarn = all_warnings(adjlst(our_graph))
+    if raerr != oaerr or rawarn != oawarn or (ra is not None and not deep_same(ra, oa)):
+        bad.append(f"AdjlstGraph differs (reference: {raerr}, this repo: {oaerr}; warnings equal: {rawarn == oawarn})")
     if not werr and want[1].size > 1:                      # .npz round trips (graph.py:447-497) and from_mat (:513-528)
         rr, _, _ = read_with(npz_and_mat(ref_graph, ref_graph))
         for label, m, src in (("read_npz of a reference file / from_mat", our_graph, ref_graph),

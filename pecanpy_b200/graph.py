@@ -3,7 +3,10 @@
 The reference's graph I/O (src/pecanpy/graph.py) is out of scope for the B200 engine and is not
 re-implemented feature for feature; these light containers exist so that the drop-in classes
 in :mod:`pecanpy_b200.pecanpy` can be constructed and loaded exactly like the reference's
-(``read_edg`` / ``read_npz`` / ``from_mat`` / ``save``; same attribute names and dtypes):
+(``read_edg`` / ``read_npz`` / ``from_mat`` / ``from_adjlst_graph`` / ``save``; same attribute names and dtypes):
+
+* ``AdjlstGraph``: the editable adjacency-list graph of reference graph.py:108-387 (``add_node`` / ``add_edge`` /
+  ``read`` / ``save`` / ``to_csr`` / ``to_dense`` / ``from_mat``)
 
 * ``SparseGraph``: CSR ``indptr`` uint32[n+1], ``indices`` uint32[nnz] (rows sorted, unique),
   ``data`` float32[nnz]   (reference graph.py:389-528, typing.py:31)
@@ -181,6 +184,117 @@ def _coo_to_csr(n: int, rows, cols, w):
     return indptr, cols.astype(np.uint32), w.astype(np.float32)
 
 
+class AdjlstGraph(BaseGraph):
+    """Editable adjacency-list graph with the observable behaviour of the reference's (graph.py:108-387): the class
+    users build or read a graph with before handing it to ``SparseGraph.from_adjlst_graph`` /
+    ``DenseGraph.from_adjlst_graph``.  Per node one dict ``neighbour index -> weight``; node order = first appearance;
+    a repeated edge overwrites (with the reference's warning when the weight changes); non-positive weights are
+    ignored with a warning; ``num_edges`` counts INSERTIONS (both directions of an undirected edge, repeats included),
+    as the reference's counter does (graph.py:238-241)."""
+
+    def __init__(self):
+        super().__init__()
+        self._data: List[Dict[int, float]] = []
+        self._num_edges = 0
+
+    @property
+    def edges_iter(self):
+        for head, nbrs in enumerate(self._data):
+            for tail in sorted(nbrs):
+                yield head, tail, nbrs[tail]
+
+    @property
+    def edges(self):
+        return list(self.edges_iter)
+
+    @property
+    def num_edges(self):
+        return self._num_edges
+
+    def add_node(self, node_id: str):
+        if node_id not in self._node_idmap:
+            self._node_idmap[node_id] = len(self._node_ids)
+            self._node_ids.append(node_id)
+            self._data.append({})
+
+    def get_node_idx(self, node_id: str) -> int:
+        self.add_node(node_id)
+        return self._node_idmap[node_id]
+
+    def _add_edge_from_idx(self, idx1: int, idx2: int, weight: float):
+        self._data[idx1][idx2] = weight
+        self._num_edges += 1
+
+    def add_edge(self, id1: str, id2: str, weight: float = 1.0, directed: bool = False):
+        if weight <= 0:                                      # graph.py:182-192
+            warnings.warn(f"Non-positive edge ignored: w({id1},{id2}) = {weight}", RuntimeWarning, stacklevel=2)
+            return
+        i, j = self.get_node_idx(id1), self.get_node_idx(id2)
+        old = self._data[i].get(j)
+        if old is not None and old != weight:                # graph.py:194-215 (checked for the forward direction only)
+            warnings.warn(f"edge from {id1} to {id2} exists, with value of {old:.2f}. Now overwrite to {weight:.2f}.",
+                          RuntimeWarning, stacklevel=2)
+        self._add_edge_from_idx(i, j, weight)
+        if not directed:
+            self._add_edge_from_idx(j, i, weight)
+
+    def read(self, path: str, weighted: bool, directed: bool, delimiter: str = "\t"):
+        """One ``add_edge`` per line, in file order (graph.py:160-180, 270-305): ``id1 <delim> id2 [<delim> weight]``."""
+        with open(path, encoding="utf-8") as f:
+            for line in f:
+                terms = line.strip().split(delimiter)
+                id1, id2 = terms[0].strip(), terms[1].strip()
+                weight = 1.0
+                if weighted:
+                    if len(terms) != 3:
+                        raise ValueError(f"Expecting three columns in the edge list file for a weighted graph, "
+                                         f"got {len(terms)} instead: {line!r}")
+                    weight = float(terms[-1])
+                self.add_edge(id1, id2, weight, directed)
+
+    def save(self, path: str, unweighted: bool = False, delimiter: str = "\t"):
+        """Edge list, one line per stored (head, tail) in index order (graph.py:307-321)."""
+        with open(path, "w", encoding="utf-8") as f:
+            for h, t, w in self.edges_iter:
+                cols = (self._node_ids[h], self._node_ids[t]) if unweighted else (self._node_ids[h], self._node_ids[t], str(w))
+                f.write(delimiter.join(cols) + "\n")
+
+    def to_csr(self):
+        """(indptr uint32, indices uint32, data float32), rows sorted (graph.py:323-341)."""
+        deg = np.fromiter((len(r) for r in self._data), dtype=np.int64, count=len(self._data))
+        indptr = np.zeros(len(self._data) + 1, dtype=np.uint32)
+        np.cumsum(deg, out=indptr[1:])
+        indices = np.zeros(int(indptr[-1]), dtype=np.uint32)
+        data = np.zeros(int(indptr[-1]), dtype=np.float32)
+        for i, nbrs in enumerate(self._data):
+            if nbrs:
+                keys = sorted(nbrs)
+                lo = int(indptr[i])
+                indices[lo:lo + len(keys)] = keys
+                data[lo:lo + len(keys)] = [nbrs[k] for k in keys]
+        return indptr, indices, data
+
+    def to_dense(self):
+        """Full float64 adjacency matrix in ``nodes`` order (graph.py:343-362)."""
+        n = len(self._node_ids)
+        mat = np.zeros((n, n))
+        for i, nbrs in enumerate(self._data):
+            if nbrs:
+                mat[i, list(nbrs)] = list(nbrs.values())
+        return mat
+
+    @classmethod
+    def from_mat(cls, adj_mat, node_ids: List[str], **kwargs):
+        """Every NONZERO entry becomes an edge, sign included, without the checks of ``add_edge`` (graph.py:364-387)."""
+        g = cls(**kwargs)
+        for node_id in node_ids:
+            g.add_node(node_id)
+        adj = np.asarray(adj_mat)
+        for i, j in zip(*np.nonzero(adj != 0)):
+            g._add_edge_from_idx(i, j, adj[i, j])
+        return g
+
+
 class SparseGraph(BaseGraph):
     def __init__(self):
         super().__init__()
@@ -229,6 +343,14 @@ class SparseGraph(BaseGraph):
         adj = np.asarray(adj_mat)
         rows, cols = np.nonzero(adj)
         g.indptr, g.indices, g.data = _coo_to_csr(adj.shape[0], rows, cols, adj[rows, cols].astype(np.float64))
+        return g
+
+    @classmethod
+    def from_adjlst_graph(cls, adjlst_graph, **kwargs):
+        """graph.py:498-511: node ids and CSR of an ``AdjlstGraph`` (this module's or the reference's)."""
+        g = cls(**kwargs)
+        g.set_node_ids(adjlst_graph.nodes)
+        g.indptr, g.indices, g.data = adjlst_graph.to_csr()
         return g
 
     @classmethod
@@ -285,6 +407,14 @@ class DenseGraph(BaseGraph):
 
     def save(self, path: str):
         np.savez(path, data=self.data, IDs=self.nodes)
+
+    @classmethod
+    def from_adjlst_graph(cls, adjlst_graph, **kwargs):
+        """graph.py:631-643: node ids and dense matrix of an ``AdjlstGraph`` (this module's or the reference's)."""
+        g = cls(**kwargs)
+        g.set_node_ids(adjlst_graph.nodes)
+        g.data = adjlst_graph.to_dense()
+        return g
 
     @classmethod
     def from_mat(cls, adj_mat, node_ids: List[str], **kwargs):

@@ -267,3 +267,37 @@ def test_strategy_seams_of_the_reference_api():
         assert [has(i) for i in range(4)] == [True, True, True, False]
         with pytest.raises(NotImplementedError):
             g.get_move_forward()
+
+
+def test_adjlst_graph_behaviour(tmp_path):
+    """AdjlstGraph / from_adjlst_graph (reference graph.py:108-387, 498-511, 631-643): first-appearance node order,
+    overwrite and non-positive warnings, the insertion counter, sorted CSR rows, save -> read round trip.  (The full
+    comparison with the reference's class runs in oracle/fuzz_reference_graph.py.)"""
+    from pecanpy_b200.graph import AdjlstGraph, DenseGraph, SparseGraph
+    g = AdjlstGraph()
+    with warnings.catch_warnings(record=True) as rec:
+        warnings.simplefilter("always")
+        g.add_edge("b", "a", 2.0)
+        g.add_edge("a", "c", 0.5, directed=True)
+        g.add_edge("x", "y", -1.0)                          # ignored: neither node is created
+        g.add_edge("b", "a", 3.0)                           # overwrites both directions
+    assert [str(r.message) for r in rec] == ["Non-positive edge ignored: w(x,y) = -1.0",
+                                             "edge from b to a exists, with value of 2.00. Now overwrite to 3.00."]
+    assert g.nodes == ["b", "a", "c"] and g.num_edges == 5                    # insertions, repeats included
+    assert g.edges == [(0, 1, 3.0), (1, 0, 3.0), (1, 2, 0.5)]
+    indptr, indices, data = g.to_csr()
+    assert indptr.dtype == np.uint32 and indptr.tolist() == [0, 1, 3, 3]
+    assert indices.tolist() == [1, 0, 2] and data.dtype == np.float32 and data.tolist() == [3.0, 3.0, 0.5]
+    assert np.array_equal(g.to_dense(), np.array([[0, 3, 0], [3, 0, 0.5], [0, 0, 0]]))
+    sp = SparseGraph.from_adjlst_graph(g)
+    dn = DenseGraph.from_adjlst_graph(g)
+    assert sp.nodes == g.nodes and np.array_equal(sp.indptr, indptr) and np.array_equal(sp.data, data)
+    assert dn.nodes == g.nodes and np.array_equal(dn.data, g.to_dense()) and dn.num_edges == 3
+    p = tmp_path / "out.edg"
+    g.save(str(p))
+    assert p.read_text() == "b\ta\t3.0\na\tb\t3.0\na\tc\t0.5\n"
+    h = AdjlstGraph()
+    h.read(str(p), weighted=True, directed=True)
+    assert h.nodes == g.nodes and h.edges == g.edges
+    m = AdjlstGraph.from_mat(np.array([[0, -2.0], [1.5, 0]]), ["u", "v"])     # no validity check: the sign stays
+    assert m.edges == [(0, 1, -2.0), (1, 0, 1.5)] and m.num_edges == 2
