@@ -12,7 +12,9 @@ What changes with respect to the reference:
 * the njit closure pair ``get_move_forward()`` / ``get_has_nbrs()`` cannot be called from a GPU;
   the strategy is selected by the class (``_MODE``) instead.  ``_random_walks`` keeps the reference's positional
   signature and ignores the two callbacks; ``get_has_nbrs()`` returns a plain host callable, ``get_move_forward()``
-  raises;
+  raises.  The njit helpers those closures call (``get_normalized_probs``, ``get_extended_normalized_probs``,
+  ``get_normalized_probs_first_order``, rw/sparse_rw.py:39-130, rw/dense_rw.py:34-118) exist only inside the CUDA
+  kernels and are not exposed as host methods: a host copy of them would be a second, CPU implementation of the path;
 * random numbers: Philox4x32-10 keyed by ``(random_state, global walker row, step)`` instead of a
   per-thread MT19937, so seeded walks are reproducible for ANY thread / GPU count (the reference
   is reproducible only at one thread, pecanpy.py:51-55).  The start-node shuffle stays on the host
