@@ -46,6 +46,12 @@ class BaseGraph:
     def density(self) -> float:
         return self.num_edges / self.num_nodes / (self.num_nodes - 1)
 
+    def get_has_nbrs(self):
+        raise NotImplementedError                # abstract, as graph.py:99-101
+
+    def get_move_forward(self):
+        raise NotImplementedError                # abstract, as graph.py:103-105
+
     def set_node_ids(self, node_ids: Optional[Sequence[str]], implicit_ids: bool = False,
                      num_nodes: Optional[int] = None):
         if node_ids is not None and not implicit_ids:

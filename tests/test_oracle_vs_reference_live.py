@@ -39,3 +39,30 @@ def test_edge_list_loaders_equal_reference_on_random_files():
                        cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert json.loads(r.stdout.strip().splitlines()[-1])["failures"] == []
+
+
+@pytest.mark.skipif(not _reference_available(), reason="the reference (or numba) is not present on this machine")
+def test_public_api_surface_equals_reference_up_to_the_documented_differences():
+    """oracle/api_surface.py: every public name of the reference's five walk classes and four graph containers exists
+    here with the same parameters and defaults, except (a) the njit helpers that live only inside the CUDA kernels,
+    (b) AdjlstGraph's private helpers, (c) _random_walks being a method with optional callbacks, (d) read_edg's extra
+    ``device`` keyword."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "api_surface.py")], cwd=ROOT, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    helpers = {"get_extended_normalized_probs", "get_normalized_probs", "get_normalized_probs_first_order",
+               "setup_get_normalized_probs"}
+    private = {"_check_edge_existence", "_is_valid_edge_weight", "_read_edge_line"}
+    for cls, names in d["missing"].items():
+        allowed = private if cls == "AdjlstGraph" else helpers
+        assert set(names) <= allowed, (cls, names)
+    for key, sig in d["signatures"].items():
+        meth = key.split(".")[1]
+        ref, ours = sig["reference"], sig["ours"]
+        if meth == "_random_walks":
+            assert [p[0] for p in ours] == ["self"] + [p[0] for p in ref]
+        elif meth == "read_edg":
+            assert ours[:len(ref)] == ref and [p[0] for p in ours[len(ref):]] == ["device"] and ours[-1][2] == "None"
+        else:
+            raise AssertionError(f"undocumented signature difference: {key}: {sig}")
