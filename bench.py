@@ -365,22 +365,24 @@ def run_workload(name, args, K, W, rank, world, local_rank, *, do_e2e=True, do_c
             cur.wait_stream(comm)
 
     if world > 4 and args.gather == "auto" and gather == "mirror":
-        probe = {}
-        for cand in ("mirror", "nccl"):                     # (NCCL gathers into the same, IPC-shared, matrix)
+        def run_with(cand, seed):                           # (NCCL gathers into the same, IPC-shared, matrix)
+            nonlocal gather
             gather = cand
-            one_pass(900)
+            one_pass(seed)
+
+        def timed_ms(fn):
             torch.cuda.synchronize()
             barrier()
             p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             p0.record()
-            one_pass(901)
-            one_pass(902)
+            fn()
             p1.record()
             torch.cuda.synchronize()
-            pt = torch.tensor([p0.elapsed_time(p1) / 2], dtype=torch.float64, device=dev)
+            pt = torch.tensor([p0.elapsed_time(p1)], dtype=torch.float64, device=dev)
             dist.all_reduce(pt, op=dist.ReduceOp.MAX)       # the same number, hence the same choice, on every rank
-            probe[cand] = float(pt[0])
-        gather = "mirror" if probe["mirror"] <= probe["nccl"] else "nccl"
+            return float(pt[0])
+
+        gather, probe = choose_gather(["mirror", "nccl"], run_with, timed_ms)
         extras["gather_probe_ms"] = probe
         log(f"[bench] rank {rank}: gather probe {probe} -> {gather}")
     for it in range(W):
@@ -545,6 +547,19 @@ def run_workload(name, args, K, W, rank, world, local_rank, *, do_e2e=True, do_c
     del eng, d_start_all, flush
     torch.cuda.empty_cache()
     return line
+
+
+def choose_gather(candidates, run_pass, timed_ms):
+    """Warm-up probe between gather mechanisms (N > 4, --gather auto): ``run_pass(cand, seed)`` runs one whole pass
+    with mechanism ``cand`` (collective: every rank calls it in the same order), ``timed_ms(fn)`` returns the device
+    time of ``fn()`` in ms, max over ranks (so every rank sees the same numbers and chooses the same).  One untimed
+    pass, then two timed ones per candidate; the first candidate wins ties.  Returns (choice, {cand: ms per pass})."""
+    probe = {}
+    for cand in candidates:
+        run_pass(cand, 900)
+        probe[cand] = timed_ms(lambda c=cand: (run_pass(c, 901), run_pass(c, 902))) / 2
+    best = min(candidates, key=lambda c: (probe[c], candidates.index(c)))
+    return best, probe
 
 
 def on_rank0_while_others_sleep(dist, rank, work, timeout_s=1800.0):

@@ -36,3 +36,26 @@ def test_cuda_arm_refuses_to_run_without_a_gpu():
     r = _run("--scale", "0.01", "--steps", "1", "--warmup", "0", "--no-extra")
     assert r.returncode != 0
     assert "needs a GPU" in r.stderr and not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_gather_probe_picks_the_faster_mechanism_and_leaves_it_selected():
+    """bench.choose_gather (N > 4, --gather auto): one warm + two timed passes per candidate, same order on every rank;
+    the faster wins, the first wins ties."""
+    sys.path.insert(0, ROOT)
+    import bench
+    for cost, want in (({"mirror": 4.7, "nccl": 7.3}, "mirror"), ({"mirror": 21.7, "nccl": 7.3}, "nccl"),
+                       ({"mirror": 5.0, "nccl": 5.0}, "mirror")):
+        calls, clock = [], [0.0]
+
+        def run_pass(cand, seed):
+            calls.append((cand, seed))
+            clock[0] += cost[cand]
+
+        def timed_ms(fn):
+            t0 = clock[0]
+            fn()
+            return clock[0] - t0
+
+        best, probe = bench.choose_gather(["mirror", "nccl"], run_pass, timed_ms)
+        assert best == want and probe == pytest.approx(cost)
+        assert calls == [("mirror", 900), ("mirror", 901), ("mirror", 902), ("nccl", 900), ("nccl", 901), ("nccl", 902)]
