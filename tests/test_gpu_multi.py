@@ -198,3 +198,29 @@ def test_allgather_rows_entry_point():
     for m in mats:
         assert torch.equal(m, want)
     assert lib.b2w_allgather_rows(0, peers, world, world, R, ld, C.c_void_p(st)) != capi.OK     # self out of range
+
+
+def test_push_rows_streams_entry_point():
+    """b2w_push_rows_streams (one stream per peer, what PeerMatrix.push uses): arbitrary row blocks of each `rank` land
+    in every other matrix; again three matrices of one GPU stand in for the mapped peers."""
+    import ctypes as C
+    import torch
+    from pecanpy_b200 import _capi as capi
+    lib = capi.lib()
+    world, R, ld = 3, 777, 33
+    mats = [torch.zeros((world * R, ld), dtype=torch.int32, device="cuda:0") for _ in range(world)]
+    for r, m in enumerate(mats):
+        m[r * R:(r + 1) * R] = torch.randint(1, 1 << 30, (R, ld), dtype=torch.int32, device="cuda:0")
+    want = torch.cat([mats[r][r * R:(r + 1) * R] for r in range(world)])
+    torch.cuda.synchronize()                                # the side streams below do not wait for the default stream
+    peers = (C.c_void_p * world)(*[m.data_ptr() for m in mats])
+    streams = [torch.cuda.Stream(device="cuda:0") for _ in range(world)]
+    sptr = (C.c_void_p * world)(*[s.cuda_stream for s in streams])
+    for r in range(world):
+        half = R // 2                                       # two pushes per rank: [r R, r R + half) and the rest
+        capi.check(lib.b2w_push_rows_streams(0, peers, world, r, r * R, half, 4 * ld, sptr), "b2w_push_rows_streams")
+        capi.check(lib.b2w_push_rows_streams(0, peers, world, r, r * R + half, R - half, 4 * ld, sptr),
+                   "b2w_push_rows_streams")
+    torch.cuda.synchronize()
+    for m in mats:
+        assert torch.equal(m, want)
